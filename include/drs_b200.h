@@ -1,0 +1,92 @@
+/*
+ * drs_b200 -- C ABI of the B200 dense-retrieval scoring engine.
+ *
+ * The reference (PM25/Information-Retrieval-with-Contrastive-Learning) is pure Python and has no
+ * FFI of its own; these entry points are what a binding for its similarity-and-select path binds
+ * (see INTEGRATION.md for the ctypes stubs).  Each function names the reference call it replaces.
+ *
+ * Conventions
+ *   - every pointer marked "device" is a CUDA device pointer owned by the caller; the library
+ *     allocates nothing and keeps no state between calls except the options set below;
+ *   - matrices are row-major and contiguous; `stream` is a cudaStream_t passed as void*
+ *     (NULL = the legacy default stream); calls are asynchronous on that stream;
+ *   - workspace: ask `*_workspace_bytes`, pass a device buffer at least that large;
+ *   - return value: DRS_OK (0) or an error code; `drs_last_error()` has the message
+ *     (thread local).  Nothing is thrown across the boundary.
+ */
+#ifndef DRS_B200_H_
+#define DRS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { DRS_OK = 0, DRS_ERR_INVALID = 1, DRS_ERR_CUDA = 2, DRS_ERR_UNSUPPORTED = 3, DRS_ERR_WORKSPACE = 4 };
+enum { DRS_F32 = 0, DRS_BF16 = 1 };
+#define DRS_MAX_K 32
+
+int drs_version(void);
+const char* drs_last_error(void);
+
+/* Test / tuning knobs.  "search.cta_group": 0 auto, 1 single CTA (128x256 MMA), 2 CTA pair
+ * (256x256 MMA).  "search.num_ctas": 0 auto (all SMs), else the persistent grid size.
+ * "search.splits": 0 auto, else the number of corpus splits. */
+int drs_set_option(const char* name, int value);
+/* Debug: {flag, tag, block, thread, parity, extra} of the last pipeline wait that timed out (a
+ * kernel whose mbarrier wait exceeds a few seconds records this in mapped host memory and traps,
+ * so a broken pipeline surfaces as a CUDA error instead of a hang).  flag == 0: none. */
+int drs_debug_hang_report(unsigned int out[6]);
+int drs_get_option(const char* name, int* value);
+
+/*
+ * Dense claim x corpus scoring with fused top-k select.
+ * Replaces: the dense scoring intended at src/evaluation.py:105-116 (dot products of ctx2vec
+ * embeddings) + the select of TfidfDocRanker.closest_docs
+ * (preprocessing/drqa/retriever/tfidf_doc_ranker.py:60-75), batched over claims like
+ * batch_closest_docs (:77-84).
+ *
+ *   queries  device [nq, dim]   dtype DRS_BF16 (tcgen05 path) or DRS_F32 (exact FFMA path)
+ *   corpus   device [nc, dim]   same dtype
+ *   out_scores device [nq, k] fp32, descending;  out_ids device [nq, k] int64 = row + id_base
+ *   ties are broken by the lower row index; when nc < k the tail is (-inf, -1).
+ * DRS_BF16 needs dim % 8 == 0 and 16-byte aligned base pointers (TMA); k <= DRS_MAX_K.
+ */
+int drs_search_workspace_bytes(int64_t nq, int64_t nc, int dim, int k, int dtype, size_t* bytes);
+int drs_search(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,
+               int64_t id_base, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+               void* stream);
+
+/*
+ * Merge the per-shard top-k lists of a row-sharded corpus (after the all-gather):
+ *   scores device [num_shards, nq, k], ids device [num_shards, nq, k] (id < 0 = empty slot)
+ *   -> out_scores / out_ids device [nq, k], ordered by (score desc, id asc).
+ * No reference counterpart (the reference is single-device); SURVEY.md section 8(e).
+ */
+int drs_merge_shards(const float* scores, const int64_t* ids, int num_shards, int64_t nq, int k, float* out_scores,
+                     int64_t* out_ids, void* stream);
+
+/*
+ * In-batch InfoNCE (SimCLR form) with fused logits + softmax cross-entropy.
+ * Replaces: NCELoss._compute_info_loss (src/contrastor/contrastive_loss.py:56-93).
+ *   q, k   device [n, dim] fp32 (L2-normalised by the caller, contrastive_module.py:111)
+ *   queue  device [dim, queue_len] fp32 or NULL (MoCo negatives, :77-82; rows n..2n-1 reuse q's
+ *          queue logits exactly like the reference's .repeat(2, 1))
+ *   precision DRS_F32: fp32 FFMA logits;  DRS_BF16: inputs rounded to bf16, tcgen05, fp32 accumulate
+ *   loss   device [1] fp32 = sum_i CE_i / 2;   lse device [2n] fp32 (saved for backward)
+ * Backward: dq, dk device [n, dim] fp32 = grad_loss[0] * dloss/d{q,k}; grad_loss device [1].
+ */
+int drs_infonce_workspace_bytes(int64_t n, int dim, int64_t queue_len, int precision, size_t* bytes);
+int drs_infonce_forward(const float* q, const float* k, const float* queue, int64_t n, int dim, int64_t queue_len,
+                        float inv_temperature, int precision, float* loss, float* lse, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int drs_infonce_backward(const float* q, const float* k, const float* queue, int64_t n, int dim, int64_t queue_len,
+                         float inv_temperature, int precision, const float* lse, const float* grad_loss, float* dq,
+                         float* dk, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRS_B200_H_ */

@@ -1,0 +1,22 @@
+"""B200-native dense-retrieval scoring engine for the FEVER contrastive-IR project.
+
+Drop-in for the query-by-document similarity-and-select path of
+PM25/Information-Retrieval-with-Contrastive-Learning:
+
+* ``search`` / ``DenseIndex`` / ``ShardedDenseIndex`` -- dense claim x corpus scores + top-k ids
+  (src/evaluation.py:105-116 call site, ``TfidfDocRanker.closest_docs`` signature);
+* ``NCELoss`` / ``info_nce_loss`` -- in-batch InfoNCE logits + softmax-CE forward/backward
+  (src/contrastor/contrastive_loss.py:47-141).
+
+Everything computes in hand-written sm_100a CUDA behind the C ABI of include/drs_b200.h
+(libdrs_b200.so, built in-tree by ``build.build()``); there is no CPU fallback.
+"""
+from . import _lib, build
+from ._lib import get_option, set_option
+from .loss import NCELoss, info_nce_loss
+from .retrieval import DenseIndex, ShardedDenseIndex, all_gather_topk, merge_shards, search, shard_bounds
+
+__all__ = [
+    "search", "merge_shards", "DenseIndex", "ShardedDenseIndex", "all_gather_topk", "shard_bounds",
+    "NCELoss", "info_nce_loss", "set_option", "get_option", "build",
+]

@@ -1,0 +1,332 @@
+// C ABI of the engine (include/drs_b200.h).  Single translation unit: kernels come in through
+// the .cuh files.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -shared ...
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+
+#include "../../include/drs_b200.h"
+#include "epilogues.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "infonce.cuh"
+#include "merge.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// mapped pinned host memory the kernels write their hang report to (survives a trapped context)
+drs::HangReport* g_hang_host = nullptr;
+
+// A launch/runtime error.  If a kernel trapped on an mbarrier timeout, say which wait it was.
+int cuda_fail(cudaError_t e, const char* what) {
+  if (g_hang_host && g_hang_host->flag) {
+    const drs::HangReport rep = *g_hang_host;
+    return fail(DRS_ERR_CUDA, "%s: %s (pipeline wait timed out: tag=%u block=%u thread=%u parity=%u extra=%u)", what,
+                cudaGetErrorString(e), rep.tag, rep.block, rep.thread, rep.parity, rep.extra);
+  }
+  return fail(DRS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+#define DRS_CUDA(call)                                  \
+  do {                                                  \
+    cudaError_t e_ = (call);                            \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+  } while (0)
+
+struct Options {
+  int cta_group = 0;
+  int num_ctas = 0;
+  int splits = 0;
+  int infonce_cta_group = 0;
+} g_opt;
+
+struct DeviceInfo {
+  int device = -1;
+  int num_sms = 0;
+  int cc_major = 0, cc_minor = 0;
+};
+int get_device_info(DeviceInfo* out) {
+  static thread_local DeviceInfo cache[64];
+  int dev = 0;
+  DRS_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(DRS_ERR_INVALID, "device ordinal %d out of range", dev);
+  if (cache[dev].device != dev) {
+    cache[dev].device = dev;
+    DRS_CUDA(cudaDeviceGetAttribute(&cache[dev].num_sms, cudaDevAttrMultiProcessorCount, dev));
+    DRS_CUDA(cudaDeviceGetAttribute(&cache[dev].cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    DRS_CUDA(cudaDeviceGetAttribute(&cache[dev].cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    if (!g_hang_host) {
+      void* h = nullptr;
+      if (cudaHostAlloc(&h, sizeof(drs::HangReport), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+        memset(h, 0, sizeof(drs::HangReport));
+        g_hang_host = static_cast<drs::HangReport*>(h);
+      }
+    }
+    if (g_hang_host) {
+      void* d = nullptr;
+      if (cudaHostGetDevicePointer(&d, g_hang_host, 0) == cudaSuccess)
+        DRS_CUDA(cudaMemcpyToSymbol(drs::g_hang_ptr, &d, sizeof(d)));
+    }
+  }
+  *out = cache[dev];
+  return DRS_OK;
+}
+
+// ------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// [rows, dim] bf16 row-major; box = 64 (K) x box_rows, 128-byte swizzle, zero fill out of bounds
+int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int dim, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(DRS_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DRS_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+  return DRS_OK;
+}
+
+// ------------------------------------------------------------------ work decomposition
+// units = num_m_tiles * splits, dealt round-robin to `groups` persistent clusters.  Pick the
+// smallest split count that makes the units a multiple of the groups (every cluster gets the same
+// number of equally long units), capped by the number of B tiles.
+drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int rows_per_m_tile, int rows_per_b_tile,
+                          int groups, int forced_splits) {
+  drs::GemmShape s;
+  s.rows_a = static_cast<int>(rows_a);
+  s.rows_b = static_cast<int>(rows_b);
+  s.num_k_blocks = dim_k_blocks;
+  s.num_m_tiles = static_cast<int>((rows_a + rows_per_m_tile - 1) / rows_per_m_tile);
+  s.total_b_tiles = static_cast<int>((rows_b + rows_per_b_tile - 1) / rows_per_b_tile);
+  int splits = forced_splits > 0 ? forced_splits : groups / std::gcd(s.num_m_tiles, groups);
+  splits = std::max(1, std::min(splits, s.total_b_tiles));
+  s.tiles_per_split = (s.total_b_tiles + splits - 1) / splits;
+  s.num_splits = (s.total_b_tiles + s.tiles_per_split - 1) / s.tiles_per_split;  // no empty split
+  return s;
+}
+
+struct SearchPlan {
+  int dtype;
+  int cg;          // bf16: CTA group
+  int kcap;        // 16 or 32
+  int grid;        // CTAs
+  drs::GemmShape shape;
+  size_t ws_bytes;
+};
+
+int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p) {
+  if (nq <= 0 || nc <= 0 || dim <= 0) return fail(DRS_ERR_INVALID, "nq, nc, dim must be positive (got %lld, %lld, %d)", (long long)nq, (long long)nc, dim);
+  if (k <= 0 || k > DRS_MAX_K) return fail(DRS_ERR_UNSUPPORTED, "k must be in [1, %d] (got %d)", DRS_MAX_K, k);
+  if (nq > 0x7fffffffLL - 512 || nc > 0x7fffffffLL - 512) return fail(DRS_ERR_UNSUPPORTED, "nq and nc must fit in int32 (shard larger corpora)");
+  DeviceInfo di;
+  if (int rc = get_device_info(&di)) return rc;
+  p->dtype = dtype;
+  p->kcap = k <= 16 ? 16 : 32;
+  if (dtype == DRS_BF16) {
+    if (di.cc_major != 10) return fail(DRS_ERR_UNSUPPORTED, "the bf16 path needs an sm_100 device (tcgen05/TMEM); this is sm_%d%d", di.cc_major, di.cc_minor);
+    if (dim % 8 != 0) return fail(DRS_ERR_INVALID, "bf16 path: dim must be a multiple of 8 (TMA 16-byte row pitch), got %d", dim);
+    int cg = g_opt.cta_group ? g_opt.cta_group : (nq > 128 ? 2 : 1);
+    if (cg != 1 && cg != 2) return fail(DRS_ERR_INVALID, "search.cta_group must be 0, 1 or 2");
+    int ctas = g_opt.num_ctas > 0 ? g_opt.num_ctas : di.num_sms;
+    ctas = std::max(cg, ctas - ctas % cg);
+    p->cg = cg;
+    p->grid = ctas;
+    p->shape = plan_shape(nq, nc, (dim + 63) / 64, 128 * cg, 256, ctas / cg, g_opt.splits);
+  } else if (dtype == DRS_F32) {
+    int ctas = g_opt.num_ctas > 0 ? g_opt.num_ctas : 2 * di.num_sms;
+    p->cg = 1;
+    p->grid = ctas;
+    p->shape = plan_shape(nq, nc, 0, 128, 128, ctas, g_opt.splits);
+  } else {
+    return fail(DRS_ERR_INVALID, "unknown dtype %d", dtype);
+  }
+  p->ws_bytes = static_cast<size_t>(nq) * p->shape.num_splits * p->kcap * sizeof(uint64_t);
+  return DRS_OK;
+}
+
+// ------------------------------------------------------------------ generic GEMM launchers
+template <int CG, class Epi>
+int launch_gemm_tc(const void* a, const void* b, int kdim, const drs::GemmShape& shp, int grid,
+                   const typename Epi::Params& ep, cudaStream_t st) {
+  using Cfg = drs::GemmCfg<CG>;
+  CUtensorMap ta, tb;
+  if (int rc = make_tmap_bf16(&ta, a, shp.rows_a, kdim, Cfg::BM)) return rc;
+  if (int rc = make_tmap_bf16(&tb, b, shp.rows_b, kdim, Cfg::BN_CTA)) return rc;
+  auto kern = drs::gemm_nt_tc_kernel<CG, Epi>;
+  DRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DRS_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, shp, ep));
+  return DRS_OK;
+}
+template <class Epi>
+int launch_gemm_tc_cg(int cg, const void* a, const void* b, int kdim, const drs::GemmShape& shp, int grid,
+                      const typename Epi::Params& ep, cudaStream_t st) {
+  return cg == 2 ? launch_gemm_tc<2, Epi>(a, b, kdim, shp, grid, ep, st)
+                 : launch_gemm_tc<1, Epi>(a, b, kdim, shp, grid, ep, st);
+}
+template <class Epi, bool B_KN>
+int launch_gemm_simt(const float* a, long long lda, const float* b, long long ldb, int kdim,
+                     const drs::GemmShape& shp, int grid, const typename Epi::Params& ep, cudaStream_t st) {
+  auto kern = drs::gemm_simt_f32_kernel<Epi, B_KN>;
+  DRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, drs::SimtCfg::SMEM_BYTES));
+  kern<<<grid, drs::SimtCfg::THREADS, drs::SimtCfg::SMEM_BYTES, st>>>(a, b, lda, ldb, kdim, shp, ep);
+  DRS_CUDA(cudaGetLastError());
+  return DRS_OK;
+}
+
+template <int CG, int KCAP>
+int launch_search_tc(const SearchPlan& p, const void* queries, const void* corpus, int dim, uint64_t* ws,
+                     cudaStream_t st) {
+  using Epi = drs::TopKEpilogue<KCAP>;
+  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, p.shape.num_splits};
+  return launch_gemm_tc<CG, Epi>(queries, corpus, dim, p.shape, p.grid, ep, st);
+}
+
+template <int KCAP>
+int launch_search_f32(const SearchPlan& p, const void* queries, const void* corpus, int dim, uint64_t* ws,
+                      cudaStream_t st) {
+  using Epi = drs::TopKEpilogue<KCAP>;
+  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, p.shape.num_splits};
+  return launch_gemm_simt<Epi, false>(static_cast<const float*>(queries), dim, static_cast<const float*>(corpus), dim,
+                                      dim, p.shape, p.grid, ep, st);
+}
+
+int launch_merge_keys(const uint64_t* ws, int64_t nq, int ncand, int k, int64_t id_base, float* out_scores,
+                      int64_t* out_ids, cudaStream_t st) {
+  const int warps_per_block = 4;
+  const int blocks = static_cast<int>((nq + warps_per_block - 1) / warps_per_block);
+  long long* ids = reinterpret_cast<long long*>(out_ids);
+  if (ncand <= 32 * 8)
+    drs::merge_keys_kernel<8><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids);
+  else if (ncand <= 32 * 24)
+    drs::merge_keys_kernel<24><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids);
+  else
+    drs::merge_keys_kernel<0><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids);
+  DRS_CUDA(cudaGetLastError());
+  return DRS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int drs_version(void) { return 100; }
+const char* drs_last_error(void) { return g_err; }
+
+int drs_debug_hang_report(unsigned int out[6]) {
+  if (!out) return fail(DRS_ERR_INVALID, "out is null");
+  memset(out, 0, 6 * sizeof(unsigned int));
+  if (g_hang_host) memcpy(out, g_hang_host, sizeof(drs::HangReport));
+  return DRS_OK;
+}
+
+int drs_set_option(const char* name, int value) {
+  if (!name) return fail(DRS_ERR_INVALID, "null option name");
+  if (!strcmp(name, "search.cta_group")) g_opt.cta_group = value;
+  else if (!strcmp(name, "search.num_ctas")) g_opt.num_ctas = value;
+  else if (!strcmp(name, "search.splits")) g_opt.splits = value;
+  else if (!strcmp(name, "infonce.cta_group")) g_opt.infonce_cta_group = value;
+  else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
+  return DRS_OK;
+}
+int drs_get_option(const char* name, int* value) {
+  if (!name || !value) return fail(DRS_ERR_INVALID, "null argument");
+  if (!strcmp(name, "search.cta_group")) *value = g_opt.cta_group;
+  else if (!strcmp(name, "search.num_ctas")) *value = g_opt.num_ctas;
+  else if (!strcmp(name, "search.splits")) *value = g_opt.splits;
+  else if (!strcmp(name, "infonce.cta_group")) *value = g_opt.infonce_cta_group;
+  else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
+  return DRS_OK;
+}
+
+int drs_search_workspace_bytes(int64_t nq, int64_t nc, int dim, int k, int dtype, size_t* bytes) {
+  if (!bytes) return fail(DRS_ERR_INVALID, "bytes is null");
+  SearchPlan p;
+  if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
+  *bytes = p.ws_bytes;
+  return DRS_OK;
+}
+
+int drs_search(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,
+               int64_t id_base, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+               void* stream) {
+  if (!queries || !corpus || !out_scores || !out_ids) return fail(DRS_ERR_INVALID, "null pointer argument");
+  SearchPlan p;
+  if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
+  if (!workspace || workspace_bytes < p.ws_bytes)
+    return fail(DRS_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", p.ws_bytes, workspace_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint64_t* ws = static_cast<uint64_t*>(workspace);
+  int rc = DRS_OK;
+  if (dtype == DRS_BF16) {
+    if ((reinterpret_cast<uintptr_t>(queries) & 15) || (reinterpret_cast<uintptr_t>(corpus) & 15))
+      return fail(DRS_ERR_INVALID, "bf16 path: queries and corpus must be 16-byte aligned");
+    if (p.cg == 1) rc = p.kcap == 16 ? launch_search_tc<1, 16>(p, queries, corpus, dim, ws, st)
+                                     : launch_search_tc<1, 32>(p, queries, corpus, dim, ws, st);
+    else           rc = p.kcap == 16 ? launch_search_tc<2, 16>(p, queries, corpus, dim, ws, st)
+                                     : launch_search_tc<2, 32>(p, queries, corpus, dim, ws, st);
+  } else {
+    rc = p.kcap == 16 ? launch_search_f32<16>(p, queries, corpus, dim, ws, st)
+                      : launch_search_f32<32>(p, queries, corpus, dim, ws, st);
+  }
+  if (rc) return rc;
+  return launch_merge_keys(ws, nq, p.shape.num_splits * p.kcap, k, id_base, out_scores, out_ids, st);
+}
+
+int drs_merge_shards(const float* scores, const int64_t* ids, int num_shards, int64_t nq, int k, float* out_scores,
+                     int64_t* out_ids, void* stream) {
+  if (!scores || !ids || !out_scores || !out_ids) return fail(DRS_ERR_INVALID, "null pointer argument");
+  if (num_shards <= 0 || nq <= 0 || k <= 0) return fail(DRS_ERR_INVALID, "num_shards, nq, k must be positive");
+  const int warps_per_block = 4;
+  const int blocks = static_cast<int>((nq + warps_per_block - 1) / warps_per_block);
+  drs::merge_pairs_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      scores, reinterpret_cast<const long long*>(ids), num_shards, (int)nq, k, out_scores,
+      reinterpret_cast<long long*>(out_ids));
+  DRS_CUDA(cudaGetLastError());
+  return DRS_OK;
+}
+
+#include "infonce_api.inc"
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// Per-row epilogue functors plugged into the GEMM mainloops (gemm_tc.cuh, gemm_simt.cuh).
+// Each functor instance lives in the registers of ONE thread that owns ONE row of A for a whole
+// unit (a contiguous range of B rows), sees the scores of that row in increasing column order,
+// 32 at a time, and flushes once at the end of the unit.
+#pragma once
+#include "topk.cuh"
+
+namespace drs {
+
+// ---------------------------------------------------------------------------------------------
+// Running top-K of one claim over a range of corpus rows.  Replaces the select of
+// TfidfDocRanker.closest_docs (preprocessing/drqa/retriever/tfidf_doc_ranker.py:67-73) for the
+// dense scores of src/evaluation.py:110-115.  Output: KCAP packed keys per (claim, split) in the
+// workspace; merge.cuh reduces the splits to the final k.
+template <int KCAP>
+struct TopKEpilogue {
+  struct Params {
+    uint64_t* ws;  // [rows_a][num_splits][KCAP]
+    int rows_a;
+    int rows_b;
+    int num_splits;
+  };
+  TopKList<KCAP> list;
+
+  __device__ __forceinline__ void begin_unit(const Params&, int, int, int) { list.reset(); }
+
+  __device__ __forceinline__ void chunk(const Params& p, int /*row*/, int col0, const uint32_t (&v)[32]) {
+    const int valid = p.rows_b - col0;  // columns >= rows_b are TMA zero fill, not corpus rows
+    float mx = -INFINITY;
+    if (valid >= 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = (j < valid) ? fmaxf(mx, __uint_as_float(v[j])) : mx;
+    }
+    // fast path: nothing in this chunk beats the current K-th best of any row of the warp
+    if (!__any_sync(0xffffffffu, mx > list.thr)) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float s = __uint_as_float(v[j]);
+      const bool hit = (j < valid) && (s > list.thr);
+      if (__any_sync(0xffffffffu, hit)) list.insert_key(hit ? make_key(s, static_cast<uint32_t>(col0 + j)) : 0ull);
+    }
+  }
+
+  __device__ __forceinline__ void end_unit(const Params& p, int row, int, int split) {
+    if (row >= p.rows_a) return;
+    uint64_t* dst = p.ws + (static_cast<size_t>(row) * p.num_splits + split) * KCAP;
+#pragma unroll
+    for (int j = 0; j < KCAP; ++j) dst[j] = list.keys[j];
+  }
+};
+
+}  // namespace drs

@@ -1,0 +1,209 @@
+// Streaming "rows x rows" bf16 GEMM on tcgen05 with a pluggable per-row epilogue.
+//
+//   S[i, j] = sum_d A[i, d] * B[j, d]      A: [rows_a, D] bf16 row-major (claims / features)
+//                                          B: [rows_b, D] bf16 row-major (corpus / features)
+//
+// The score matrix never leaves the SM: TMA stages 64-wide K slices of A and B in 128B-swizzled
+// shared memory, one thread issues tcgen05.mma into a double-buffered 128 x 256 fp32 accumulator
+// in TMEM, and four epilogue warps read it back with tcgen05.ld, ONE ROW OF A PER THREAD, and feed
+// 32-column chunks to the epilogue functor (running top-k, online log-sum-exp, ...) while the
+// tensor core is already working on the next tile.
+//
+// Work decomposition (persistent, static): the B rows are cut into `num_splits` contiguous ranges
+// of `tiles_per_split` 256-row tiles; a unit is (split s, A tile m); cluster c runs units
+// c, c+G, c+2G, ...  Unit u = s * num_m_tiles + m, so clusters that run at the same time share the
+// same B range and stream it in lockstep: the corpus is read from HBM about once and the other
+// A tiles hit it in L2.  The epilogue functor keeps its per-row state (e.g. the top-k list) in
+// registers for the whole unit and flushes once per unit.
+//
+// CG = 1: one CTA per unit, MMA 128 x 256 x 16.   CG = 2: a CTA pair per unit, cta_group::2 MMA
+// 256 x 256 x 16, each CTA stages its own 128 rows of A and HALF of the B tile (128 rows).
+#pragma once
+#include "ptx.cuh"
+
+namespace drs {
+
+struct GemmShape {
+  int rows_a;
+  int rows_b;
+  int num_k_blocks;     // ceil(D / 64)
+  int num_m_tiles;      // ceil(rows_a / (128 * CG))
+  int num_splits;       // S
+  int tiles_per_split;  // 256-row B tiles per split
+  int total_b_tiles;    // ceil(rows_b / 256)
+};
+
+template <int CG>
+struct GemmCfg {
+  static constexpr int BM = 128;          // A rows per CTA (= TMEM lanes)
+  static constexpr int BN = 256;          // B rows per tile (= TMEM columns per accumulator stage)
+  static constexpr int BN_CTA = BN / CG;  // B rows staged by one CTA
+  static constexpr int BK = 64;           // K slice: 64 bf16 = one 128-byte swizzle row
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN_CTA * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (CG == 1) ? 4 : 6;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int THREADS = 256;
+  static constexpr uint32_t TMEM_COLS = 512;
+};
+
+// Tags reported by a timed-out mbarrier wait (see ptx.cuh)
+enum : uint32_t { kTagProducerEmpty = 1, kTagMmaFull = 2, kTagMmaTmemEmpty = 3, kTagEpiTmemFull = 4 };
+
+// Epi requirements:
+//   struct Params;                                        (trivially copyable, passed by value)
+//   __device__ void begin_unit(const Params&, int row, int m_tile, int split);
+//   __device__ void chunk(const Params&, int row, int col0, const uint32_t (&v)[32]);   fp32 bit patterns
+//   __device__ void end_unit(const Params&, int row, int m_tile, int split);
+template <int CG, class Epi>
+__global__ void __launch_bounds__(256, 1)
+gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const GemmShape shp, const typename Epi::Params ep) {
+  using Cfg = GemmCfg<CG>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * Cfg::STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const uint32_t cluster = (CG == 2) ? cluster_id_x() : blockIdx.x;
+  const uint32_t nclusters = (CG == 2) ? num_clusters_x() : gridDim.x;
+  const int num_units = shp.num_m_tiles * shp.num_splits;
+  const int nkb = shp.num_k_blocks;
+
+  if (CG == 2) cluster_sync_all();  // both CTAs of the pair are resident before the paired TMEM alloc
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], CG);  // CG==2: leader's own arrive + the peer's remote arrive
+      mbar_init(&empty_bar[i], 1);  // one tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);          // one tcgen05.commit
+      mbar_init(&tmem_empty_bar[a], CG * 128);  // every epilogue thread of the unit (leader's barrier)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<CG>(tmem_ptr_smem, Cfg::TMEM_COLS);
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (one thread)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int u = cluster; u < num_units; u += nclusters) {
+        const int m = u % shp.num_m_tiles, s = u / shp.num_m_tiles;
+        const int t0 = s * shp.tiles_per_split;
+        const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
+        const int row_a = (m * CG + static_cast<int>(cta_rank)) * Cfg::BM;
+        for (int t = t0; t < t1; ++t) {
+          const int row_b = t * Cfg::BN + static_cast<int>(cta_rank) * Cfg::BN_CTA;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u, kTagProducerEmpty, stage);
+            void* dst_a = smem_a + stage * Cfg::A_BYTES;
+            void* dst_b = smem_b + stage * Cfg::B_BYTES;
+            if constexpr (CG == 1) {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              tma_load_2d(dst_a, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
+              tma_load_2d(dst_b, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, kEvictNormal);
+            } else {
+              tma_load_2d_pair(dst_a, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
+              tma_load_2d_pair(dst_b, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, kEvictNormal);
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              else mbar_arrive_cluster(&full_bar[stage], 0);
+            }
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread, leader CTA)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(128 * CG, Cfg::BN);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int u = cluster; u < num_units; u += nclusters) {
+        const int s = u / shp.num_m_tiles;
+        const int t0 = s * shp.tiles_per_split;
+        const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
+        for (int t = t0; t < t1; ++t, ++it) {
+          const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+          mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, kTagMmaTmemEmpty, acc);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * Cfg::BN;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full_bar[stage], phase, kTagMmaFull, stage);
+            tc_fence_after();
+            const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::A_BYTES));
+            const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::B_BYTES));
+#pragma unroll
+            for (int k = 0; k < Cfg::BK / 16; ++k) {
+              // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: start address field += 2
+              umma_bf16<CG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit<CG>(&empty_bar[stage]);                       // smem slot free once these MMAs retire
+            if (kb == nkb - 1) umma_commit<CG>(&tmem_full_bar[acc]);  // accumulator complete
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue: 4 warps, one A row per thread
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int row_in_tile = quad * 32 + lane;
+    Epi epi;
+    uint32_t it = 0;
+    for (int u = cluster; u < num_units; u += nclusters) {
+      const int m = u % shp.num_m_tiles, s = u / shp.num_m_tiles;
+      const int t0 = s * shp.tiles_per_split;
+      const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
+      const int row = (m * CG + static_cast<int>(cta_rank)) * Cfg::BM + row_in_tile;
+      epi.begin_unit(ep, row, m, s);
+      for (int t = t0; t < t1; ++t, ++it) {
+        const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tmem_full_bar[acc], acc_phase, kTagEpiTmemFull, acc);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::BN;
+#pragma unroll 1
+        for (int c = 0; c < Cfg::BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, v);  // includes tcgen05.wait::ld
+          if (c == Cfg::BN / 32 - 1) {
+            // the whole accumulator stage is now in registers: hand it back to the MMA warp
+            tc_fence_before();
+            if (CG == 1 || leader) mbar_arrive(&tmem_empty_bar[acc]);
+            else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+          }
+          epi.chunk(ep, row, t * Cfg::BN + c * 32, v);
+        }
+      }
+      epi.end_unit(ep, row, m, s);
+    }
+  }
+
+  __syncwarp();  // reconverge the single-thread roles before the aligned barriers below
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+}
+
+}  // namespace drs

@@ -1,0 +1,111 @@
+// Final selects: reduce the per-split candidate keys of one claim to its k best, and merge the
+// per-shard (score, id) lists gathered from the other GPUs.  Order: score desc, id asc.
+// One warp per claim.  Keys/pairs are unique per claim, so "the best candidate strictly worse
+// than the previous pick" walks the order without mutating the candidate set.
+#pragma once
+#include "topk.cuh"
+
+namespace drs {
+
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint64_t w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w > v ? w : v;
+  }
+  return v;
+}
+
+// ws: [nq][ncand] packed keys (0 = empty).  out_scores [nq][k] fp32, out_ids [nq][k] int64
+// (local row + id_base; -1 and -inf pad when fewer than k candidates exist).
+// LCAP: candidates cached per lane in registers (ncand <= 32 * LCAP), else re-read from L2.
+template <int LCAP>
+__global__ void __launch_bounds__(128)
+merge_keys_kernel(const uint64_t* __restrict__ ws, int nq, int ncand, int k, long long id_base,
+                  float* __restrict__ out_scores, long long* __restrict__ out_ids) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const uint64_t* src = ws + static_cast<size_t>(q) * ncand;
+  uint64_t mine[LCAP > 0 ? LCAP : 1];
+  if constexpr (LCAP > 0) {
+#pragma unroll
+    for (int i = 0; i < LCAP; ++i) {
+      const int c = lane + 32 * i;
+      mine[i] = c < ncand ? src[c] : 0ull;
+    }
+  }
+  uint64_t prev = ~0ull;
+  for (int r = 0; r < k; ++r) {
+    uint64_t best = 0ull;
+    if constexpr (LCAP > 0) {
+#pragma unroll
+      for (int i = 0; i < LCAP; ++i) {
+        const uint64_t key = mine[i];
+        if (key < prev && key > best) best = key;
+      }
+    } else {
+      for (int c = lane; c < ncand; c += 32) {
+        const uint64_t key = __ldg(src + c);
+        if (key < prev && key > best) best = key;
+      }
+    }
+    best = warp_max_u64(best);
+    if (lane == 0) {
+      out_scores[static_cast<size_t>(q) * k + r] = best ? key_score(best) : -INFINITY;
+      out_ids[static_cast<size_t>(q) * k + r] = best ? static_cast<long long>(key_index(best)) + id_base : -1ll;
+    }
+    prev = best;  // best == 0 -> nothing is < 0: the remaining picks are all empty
+  }
+}
+
+// (score, id) pair order: a is better than b
+__device__ __forceinline__ bool pair_better(float sa, long long ia, float sb, long long ib) {
+  return (sa > sb) || (sa == sb && ia < ib);
+}
+
+// Merge g lists per claim: scores [g][nq][k], ids [g][nq][k] (id < 0 = empty) -> [nq][k].
+__global__ void __launch_bounds__(128)
+merge_pairs_kernel(const float* __restrict__ in_scores, const long long* __restrict__ in_ids, int g, int nq, int k,
+                   float* __restrict__ out_scores, long long* __restrict__ out_ids) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const int ncand = g * k;
+  float ps = INFINITY;
+  long long pi = -1;  // previous pick; (inf, -1) is better than every real candidate
+  for (int r = 0; r < k; ++r) {
+    float bs = -INFINITY;
+    long long bi = -1;  // -1 = none yet
+    for (int c = lane; c < ncand; c += 32) {
+      const int shard = c / k, j = c - shard * k;
+      const size_t off = (static_cast<size_t>(shard) * nq + q) * k + j;
+      const long long id = in_ids[off];
+      if (id < 0) continue;
+      const float sc = in_scores[off];
+      if (!pair_better(ps, pi, sc, id)) continue;  // not strictly worse than the previous pick
+      if (bi < 0 || pair_better(sc, id, bs, bi)) { bs = sc; bi = id; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || pair_better(os, oi, bs, bi))) { bs = os; bi = oi; }
+    }
+    if (lane == 0) {
+      out_scores[static_cast<size_t>(q) * k + r] = bi >= 0 ? bs : -INFINITY;
+      out_ids[static_cast<size_t>(q) * k + r] = bi;
+    }
+    if (bi < 0) {  // exhausted: pad the rest
+      for (int rr = r + 1 + lane; rr < k; rr += 32) {
+        out_scores[static_cast<size_t>(q) * k + rr] = -INFINITY;
+        out_ids[static_cast<size_t>(q) * k + rr] = -1;
+      }
+      break;
+    }
+    ps = bs;
+    pi = bi;
+  }
+}
+
+}  // namespace drs

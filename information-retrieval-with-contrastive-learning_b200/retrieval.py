@@ -1,0 +1,221 @@
+"""Dense claim x corpus retrieval: scores and top-k ids.
+
+Host-side mirror of the reference's score-and-select interface.  The reference's dense call
+site is the commented-out block at src/evaluation.py:105-116 (``ctx2vec`` embeddings, dot
+products); its live score+select signature is ``TfidfDocRanker.closest_docs(query, k) ->
+(doc_ids, doc_scores)`` and ``batch_closest_docs``
+(preprocessing/drqa/retriever/tfidf_doc_ranker.py:60-84).  ``DenseIndex`` keeps those names,
+argument meaning and return shapes; ``search`` is the tensor-level call underneath.
+
+All arithmetic runs in the CUDA extension (csrc/): a tcgen05 bf16 score GEMM (or an fp32 FFMA
+GEMM for exact comparison) with the top-k select fused into its epilogue.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.DRS_F32, torch.bfloat16: _lib.DRS_BF16}
+
+# one cached workspace per (device, stream) so steady-state searches allocate nothing
+_workspaces: dict = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def _check_matrix(name: str, t: torch.Tensor):
+    if not isinstance(t, torch.Tensor) or t.dim() != 2:
+        raise ValueError(f"{name} must be a 2-D tensor, got {type(t).__name__} with shape {getattr(t, 'shape', None)}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device: drs_b200 has no CPU path")
+    if t.dtype not in _DTYPES:
+        raise TypeError(f"{name} must be float32 or bfloat16, got {t.dtype}")
+
+
+def search(queries: torch.Tensor, corpus: torch.Tensor, k: int, *, id_base: int = 0):
+    """Top-k corpus rows per query by dot product.
+
+    queries [nq, D], corpus [Nc, D]: CUDA, row-major, same dtype (bf16 -> tcgen05 path, scores
+    within 2e-2 relative of fp32; fp32 -> exact FFMA path, 1e-5).  Rows are expected to be
+    L2-normalised the way ``seq2vec`` does (src/contrastor/contrastive_module.py:111), so the dot
+    product is the cosine; nothing here depends on that.
+
+    Returns (scores fp32 [nq, k'], ids int64 [nq, k']) with k' = min(k, Nc) (like closest_docs,
+    tfidf_doc_ranker.py:67-68, fewer rows than k returns them all), sorted by score descending,
+    ties broken by the lower row index; ids = row index + id_base.
+    """
+    _check_matrix("queries", queries)
+    _check_matrix("corpus", corpus)
+    if queries.device != corpus.device:
+        raise RuntimeError(f"queries ({queries.device}) and corpus ({corpus.device}) must be on the same device")
+    if queries.shape[1] != corpus.shape[1]:
+        raise ValueError(f"dimension mismatch: queries {tuple(queries.shape)} vs corpus {tuple(corpus.shape)}")
+    if queries.dtype != corpus.dtype:
+        queries = queries.to(corpus.dtype)
+    if k <= 0:
+        raise ValueError(f"k must be positive, got {k}")
+    nq, dim = queries.shape
+    nc = corpus.shape[0]
+    kk = min(int(k), nc)
+    dev = queries.device
+    if nq == 0 or nc == 0:
+        return (torch.empty(nq, kk, dtype=torch.float32, device=dev), torch.empty(nq, kk, dtype=torch.int64, device=dev))
+    if kk > _lib.DRS_MAX_K:
+        raise RuntimeError(f"k={kk} exceeds the engine limit of {_lib.DRS_MAX_K}")
+    queries = queries.contiguous()
+    corpus = corpus.contiguous()
+    lib = _lib.load()
+    dt = _DTYPES[corpus.dtype]
+    with torch.cuda.device(dev):
+        need = ctypes.c_size_t(0)
+        _lib.check(lib.drs_search_workspace_bytes(nq, nc, dim, kk, dt, ctypes.byref(need)))
+        ws = _workspace(dev, need.value)
+        scores = torch.empty(nq, kk, dtype=torch.float32, device=dev)
+        ids = torch.empty(nq, kk, dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.drs_search(queries.data_ptr(), nq, corpus.data_ptr(), nc, dim, dt, kk, int(id_base),
+                                  scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    return scores, ids
+
+
+def merge_shards(scores: torch.Tensor, ids: torch.Tensor):
+    """[g, nq, k] per-shard lists (id < 0 = empty) -> [nq, k] by (score desc, id asc)."""
+    if scores.dim() != 3 or scores.shape != ids.shape:
+        raise ValueError("scores and ids must both be [num_shards, nq, k]")
+    if not scores.is_cuda:
+        raise RuntimeError("merge_shards needs CUDA tensors: drs_b200 has no CPU path")
+    g, nq, k = scores.shape
+    scores = scores.contiguous().float()
+    ids = ids.contiguous().long()
+    out_s = torch.empty(nq, k, dtype=torch.float32, device=scores.device)
+    out_i = torch.empty(nq, k, dtype=torch.int64, device=scores.device)
+    if nq == 0 or k == 0:
+        return out_s, out_i
+    with torch.cuda.device(scores.device):
+        stream = torch.cuda.current_stream(scores.device).cuda_stream
+        _lib.check(_lib.load().drs_merge_shards(scores.data_ptr(), ids.data_ptr(), g, nq, k, out_s.data_ptr(),
+                                                out_i.data_ptr(), stream))
+    return out_s, out_i
+
+
+def shard_bounds(num_rows: int, rank: int, world_size: int):
+    """contiguous row shards, rank r owns [r*ceil(N/g), min(N, (r+1)*ceil(N/g)))."""
+    per = -(-num_rows // world_size)
+    lo = min(num_rows, rank * per)
+    return lo, min(num_rows, lo + per)
+
+
+class DenseIndex:
+    """A resident corpus of embeddings with the ``TfidfDocRanker`` query surface.
+
+    embeddings : [Nc, D] tensor (moved to ``device``; stored as ``dtype``, default bf16)
+    doc_ids    : optional list mapping row -> doc id, the ``doc_dict[1]`` of the reference
+                 (tfidf_doc_ranker.py:52-58); defaults to the row number
+    id_base    : global row number of this shard's first row (row-sharded corpora)
+    """
+
+    def __init__(self, embeddings: torch.Tensor, doc_ids: Optional[Sequence] = None, *, device=None,
+                 dtype: torch.dtype = torch.bfloat16, id_base: int = 0):
+        if device is None:
+            device = embeddings.device if embeddings.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.embeddings = embeddings.to(device=self.device, dtype=dtype).contiguous()
+        self.id_base = int(id_base)
+        self.num_docs = self.embeddings.shape[0]
+        if doc_ids is not None and len(doc_ids) != self.num_docs:
+            raise ValueError("doc_ids must have one entry per corpus row")
+        self.doc_dict = None
+        if doc_ids is not None:
+            self.doc_dict = ({d: i for i, d in enumerate(doc_ids)}, list(doc_ids))
+
+    # -- tfidf_doc_ranker.py:52-58
+    def get_doc_index(self, doc_id):
+        return self.doc_dict[0][doc_id] if self.doc_dict else int(doc_id)
+
+    def get_doc_id(self, doc_index):
+        return self.doc_dict[1][doc_index] if self.doc_dict else int(doc_index)
+
+    def search(self, queries: torch.Tensor, k: int = 1):
+        """queries [nq, D] on any device (host tensors are copied in) -> device (scores, ids)."""
+        q = queries.to(device=self.device, dtype=self.embeddings.dtype, non_blocking=True)
+        return search(q, self.embeddings, k, id_base=self.id_base)
+
+    def closest_docs(self, query: torch.Tensor, k: int = 1):
+        """tfidf_doc_ranker.py:60-75 -- one query vector [D] -> (list of doc ids, np.ndarray scores)."""
+        res = self.batch_closest_docs(query.reshape(1, -1), k)
+        return res[0]
+
+    def batch_closest_docs(self, queries: torch.Tensor, k: int = 1, num_workers=None):
+        """tfidf_doc_ranker.py:77-84 -- a batch of query vectors [nq, D] -> list of
+        (doc_ids, doc_scores).  ``num_workers`` is accepted and ignored (one GPU launch)."""
+        scores, ids = self.search(queries, k)
+        scores = scores.cpu().numpy().astype(np.float64)      # closest_docs returns f64 scores
+        ids = ids.cpu().numpy()
+        out = []
+        for s_row, i_row in zip(scores, ids):
+            keep = i_row >= 0
+            out.append(([self.get_doc_id(int(i) - self.id_base) for i in i_row[keep]], s_row[keep]))
+        return out
+
+
+class ShardedDenseIndex:
+    """Row-sharded corpus over the ranks of a torch.distributed group (one process per GPU).
+
+    Each rank holds rows ``shard_bounds(N, rank, world)`` and runs the same fused kernel on
+    them; the per-rank (score, global id) lists are all-gathered (NCCL over NVLink on GPUs;
+    any backend works) and merged on the GPU by (score desc, id asc), which makes the result
+    identical to a single-GPU search of the whole corpus.
+    """
+
+    def __init__(self, local_embeddings: torch.Tensor, total_rows: int, *, group=None, device=None,
+                 dtype: torch.dtype = torch.bfloat16):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        lo, hi = shard_bounds(total_rows, self.rank, self.world)
+        if local_embeddings.shape[0] != hi - lo:
+            raise ValueError(f"rank {self.rank} must hold rows [{lo}, {hi}) = {hi - lo} rows, got {local_embeddings.shape[0]}")
+        self.total_rows = total_rows
+        self.local = DenseIndex(local_embeddings, device=device, dtype=dtype, id_base=lo)
+
+    def search(self, queries: torch.Tensor, k: int = 1):
+        kk = min(int(k), self.total_rows)
+        s, i = self.local.search(queries, min(kk, max(self.local.num_docs, 1))) if self.local.num_docs else (None, None)
+        nq = queries.shape[0]
+        dev = self.local.device
+        # fixed-size slots so every rank contributes the same number of bytes
+        slot_s = torch.full((nq, kk), float("-inf"), dtype=torch.float32, device=dev)
+        slot_i = torch.full((nq, kk), -1, dtype=torch.int64, device=dev)
+        if s is not None:
+            slot_s[:, : s.shape[1]] = s
+            slot_i[:, : i.shape[1]] = i
+        if self.world == 1:
+            return slot_s, slot_i
+        all_s, all_i = all_gather_topk(slot_s, slot_i, self.group)
+        return merge_shards(all_s, all_i)
+
+
+def all_gather_topk(slot_s: torch.Tensor, slot_i: torch.Tensor, group=None):
+    """The one exchange step of the sharded path: every rank contributes its [nq, k] scores and
+    global ids; returns the stacked [world, nq, k] tensors (same on every rank)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    all_s = torch.empty((world,) + tuple(slot_s.shape), dtype=slot_s.dtype, device=slot_s.device)
+    all_i = torch.empty((world,) + tuple(slot_i.shape), dtype=slot_i.dtype, device=slot_i.device)
+    dist.all_gather_into_tensor(all_s, slot_s.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i, slot_i.contiguous(), group=group)
+    return all_s, all_i
