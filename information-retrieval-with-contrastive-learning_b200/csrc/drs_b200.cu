@@ -120,7 +120,7 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int dim, int 
 // smallest split count that makes the units a multiple of the groups (every cluster gets the same
 // number of equally long units), capped by the number of B tiles.
 drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int rows_per_m_tile, int rows_per_b_tile,
-                          int groups, int forced_splits) {
+                          int groups, int forced_splits, int col_groups) {
   drs::GemmShape s;
   s.rows_a = static_cast<int>(rows_a);
   s.rows_b = static_cast<int>(rows_b);
@@ -131,13 +131,18 @@ drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int 
   splits = std::max(1, std::min(splits, s.total_b_tiles));
   s.tiles_per_split = (s.total_b_tiles + splits - 1) / splits;
   s.num_splits = (s.total_b_tiles + s.tiles_per_split - 1) / s.tiles_per_split;  // no empty split
+  s.col_groups = col_groups;
   return s;
 }
+
+constexpr int kTcColGroups = drs::GemmCfg<1>::EPI_GROUPS;
+inline int num_slots(const drs::GemmShape& s) { return s.num_splits * s.col_groups; }
 
 struct SearchPlan {
   int dtype;
   int cg;          // bf16: CTA group
   int kcap;        // 16 or 32
+  int k;
   int grid;        // CTAs
   drs::GemmShape shape;
   size_t ws_bytes;
@@ -150,6 +155,7 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
   DeviceInfo di;
   if (int rc = get_device_info(&di)) return rc;
   p->dtype = dtype;
+  p->k = k;
   p->kcap = k <= 16 ? 16 : 32;
   if (dtype == DRS_BF16) {
     if (di.cc_major != 10) return fail(DRS_ERR_UNSUPPORTED, "the bf16 path needs an sm_100 device (tcgen05/TMEM); this is sm_%d%d", di.cc_major, di.cc_minor);
@@ -160,16 +166,16 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
     ctas = std::max(cg, ctas - ctas % cg);
     p->cg = cg;
     p->grid = ctas;
-    p->shape = plan_shape(nq, nc, (dim + 63) / 64, 128 * cg, 256, ctas / cg, g_opt.splits);
+    p->shape = plan_shape(nq, nc, (dim + 63) / 64, 128 * cg, 256, ctas / cg, g_opt.splits, kTcColGroups);
   } else if (dtype == DRS_F32) {
     int ctas = g_opt.num_ctas > 0 ? g_opt.num_ctas : 2 * di.num_sms;
     p->cg = 1;
     p->grid = ctas;
-    p->shape = plan_shape(nq, nc, 0, 128, 128, ctas, g_opt.splits);
+    p->shape = plan_shape(nq, nc, 0, 128, 128, ctas, g_opt.splits, 1);
   } else {
     return fail(DRS_ERR_INVALID, "unknown dtype %d", dtype);
   }
-  p->ws_bytes = static_cast<size_t>(nq) * p->shape.num_splits * p->kcap * sizeof(uint64_t);
+  p->ws_bytes = static_cast<size_t>(nq) * num_slots(p->shape) * p->kcap * sizeof(uint64_t);
   return DRS_OK;
 }
 
@@ -219,7 +225,7 @@ template <int CG, int KCAP>
 int launch_search_tc(const SearchPlan& p, const void* queries, const void* corpus, int dim, uint64_t* ws,
                      cudaStream_t st) {
   using Epi = drs::TopKEpilogue<KCAP>;
-  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, p.shape.num_splits};
+  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), p.k};
   return launch_gemm_tc<CG, Epi>(queries, corpus, dim, p.shape, p.grid, ep, st);
 }
 
@@ -227,7 +233,7 @@ template <int KCAP>
 int launch_search_f32(const SearchPlan& p, const void* queries, const void* corpus, int dim, uint64_t* ws,
                       cudaStream_t st) {
   using Epi = drs::TopKEpilogue<KCAP>;
-  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, p.shape.num_splits};
+  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), p.k};
   return launch_gemm_simt<Epi, false>(static_cast<const float*>(queries), dim, static_cast<const float*>(corpus), dim,
                                       dim, p.shape, p.grid, ep, st);
 }
@@ -241,6 +247,8 @@ int launch_merge_keys(const uint64_t* ws, int64_t nq, int ncand, int k, int64_t 
     drs::merge_keys_kernel<8><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids);
   else if (ncand <= 32 * 24)
     drs::merge_keys_kernel<24><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids);
+  else if (ncand <= 32 * 40)
+    drs::merge_keys_kernel<40><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids);
   else
     drs::merge_keys_kernel<0><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids);
   DRS_CUDA(cudaGetLastError());
@@ -311,7 +319,7 @@ int drs_search(const void* queries, int64_t nq, const void* corpus, int64_t nc, 
                       : launch_search_f32<32>(p, queries, corpus, dim, ws, st);
   }
   if (rc) return rc;
-  return launch_merge_keys(ws, nq, p.shape.num_splits * p.kcap, k, id_base, out_scores, out_ids, st);
+  return launch_merge_keys(ws, nq, num_slots(p.shape) * p.kcap, k, id_base, out_scores, out_ids, st);
 }
 
 int drs_merge_shards(const float* scores, const int64_t* ids, int num_shards, int64_t nq, int k, float* out_scores,

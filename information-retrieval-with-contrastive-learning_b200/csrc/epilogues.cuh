@@ -15,10 +15,11 @@ namespace drs {
 template <int KCAP>
 struct TopKEpilogue {
   struct Params {
-    uint64_t* ws;  // [rows_a][num_splits][KCAP]
+    uint64_t* ws;  // [rows_a][num_slots][KCAP]   slot = split * (column groups per tile) + group
     int rows_a;
     int rows_b;
-    int num_splits;
+    int num_slots;
+    int k;
   };
   TopKList<KCAP> list;
 
@@ -26,29 +27,35 @@ struct TopKEpilogue {
 
   __device__ __forceinline__ void chunk(const Params& p, int /*row*/, int col0, const uint32_t (&v)[32]) {
     const int valid = p.rows_b - col0;  // columns >= rows_b are TMA zero fill, not corpus rows
-    float mx = -INFINITY;
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
     if (valid >= 32) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+      for (int j = 0; j < 32; j += 4) {
+        m0 = fmaxf(m0, __uint_as_float(v[j + 0]));
+        m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+        m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+        m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+      }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mx = (j < valid) ? fmaxf(mx, __uint_as_float(v[j])) : mx;
+      for (int j = 0; j < 32; ++j) m0 = (j < valid) ? fmaxf(m0, __uint_as_float(v[j])) : m0;
     }
-    // fast path: nothing in this chunk beats the current K-th best of any row of the warp
+    const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    // fast path: nothing in this chunk beats the current k-th best of any row of the warp
     if (!__any_sync(0xffffffffu, mx > list.thr)) return;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float s = __uint_as_float(v[j]);
       const bool hit = (j < valid) && (s > list.thr);
-      if (__any_sync(0xffffffffu, hit)) list.insert_key(hit ? make_key(s, static_cast<uint32_t>(col0 + j)) : 0ull);
+      if (__any_sync(0xffffffffu, hit)) list.insert(hit ? s : -INFINITY, static_cast<uint32_t>(col0 + j), p.k);
     }
   }
 
-  __device__ __forceinline__ void end_unit(const Params& p, int row, int, int split) {
+  __device__ __forceinline__ void end_unit(const Params& p, int row, int, int slot) {
     if (row >= p.rows_a) return;
-    uint64_t* dst = p.ws + (static_cast<size_t>(row) * p.num_splits + split) * KCAP;
+    uint64_t* dst = p.ws + (static_cast<size_t>(row) * p.num_slots + slot) * KCAP;
 #pragma unroll
-    for (int j = 0; j < KCAP; ++j) dst[j] = list.keys[j];
+    for (int j = 0; j < KCAP; ++j) dst[j] = list.key(j);
   }
 };
 

@@ -176,7 +176,7 @@ gemm_simt_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, l
       }
       // the next tile's first __syncthreads (top of its K loop) orders this scan before Ts is rewritten
     }
-    if (tid < C::BM) epi.end_unit(ep, row0 + tid, m, s);
+    if (tid < C::BM) epi.end_unit(ep, row0 + tid, m, s);  // one column group: slot == split
   }
 }
 

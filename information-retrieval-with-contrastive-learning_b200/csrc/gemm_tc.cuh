@@ -5,9 +5,10 @@
 //
 // The score matrix never leaves the SM: TMA stages 64-wide K slices of A and B in 128B-swizzled
 // shared memory, one thread issues tcgen05.mma into a double-buffered 128 x 256 fp32 accumulator
-// in TMEM, and four epilogue warps read it back with tcgen05.ld, ONE ROW OF A PER THREAD, and feed
-// 32-column chunks to the epilogue functor (running top-k, online log-sum-exp, ...) while the
-// tensor core is already working on the next tile.
+// in TMEM, and eight epilogue warps (two per TMEM lane quadrant, each taking half of the tile's
+// columns) read it back with tcgen05.ld, ONE ROW OF A PER THREAD, and feed 32-column chunks to
+// the epilogue functor (running top-k, online log-sum-exp, ...) while the tensor core is already
+// working on the next tile.
 //
 // Work decomposition (persistent, static): the B rows are cut into `num_splits` contiguous ranges
 // of `tiles_per_split` 256-row tiles; a unit is (split s, A tile m); cluster c runs units
@@ -31,6 +32,7 @@ struct GemmShape {
   int num_splits;       // S
   int tiles_per_split;  // 256-row B tiles per split
   int total_b_tiles;    // ceil(rows_b / 256)
+  int col_groups;       // epilogue threads per A row (each owns a column group of every tile)
 };
 
 template <int CG>
@@ -45,7 +47,10 @@ struct GemmCfg {
   static constexpr int STAGES = (CG == 1) ? 4 : 6;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
-  static constexpr int THREADS = 256;
+  static constexpr int EPI_GROUPS = 2;     // epilogue warps per TMEM lane quadrant
+  static constexpr int EPI_THREADS = 128 * EPI_GROUPS;
+  static constexpr int THREADS = 128 + EPI_THREADS;
+  static constexpr int CHUNKS_PER_GROUP = BN / 32 / EPI_GROUPS;
   static constexpr uint32_t TMEM_COLS = 512;
 };
 
@@ -56,9 +61,9 @@ enum : uint32_t { kTagProducerEmpty = 1, kTagMmaFull = 2, kTagMmaTmemEmpty = 3, 
 //   struct Params;                                        (trivially copyable, passed by value)
 //   __device__ void begin_unit(const Params&, int row, int m_tile, int split);
 //   __device__ void chunk(const Params&, int row, int col0, const uint32_t (&v)[32]);   fp32 bit patterns
-//   __device__ void end_unit(const Params&, int row, int m_tile, int split);
+//   __device__ void end_unit(const Params&, int row, int m_tile, int slot);     slot = split * col_groups + group
 template <int CG, class Epi>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(GemmCfg<CG>::THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmShape shp, const typename Epi::Params ep) {
   using Cfg = GemmCfg<CG>;
@@ -95,7 +100,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);          // one tcgen05.commit
-      mbar_init(&tmem_empty_bar[a], CG * 128);  // every epilogue thread of the unit (leader's barrier)
+      mbar_init(&tmem_empty_bar[a], CG * Cfg::EPI_THREADS);  // every epilogue thread of the unit (leader's barrier)
     }
     fence_mbar_init();
   }
@@ -167,8 +172,9 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue: 4 warps, one A row per thread
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    // ------------------------------------------------------------ epilogue: 8 warps, one A row per thread
+    const int quad = warp & 3;         // TMEM lane quadrant this warp may read (warp id mod 4)
+    const int group = (warp - 4) >> 2; // which column group of every tile this warp owns
     const int row_in_tile = quad * 32 + lane;
     Epi epi;
     uint32_t it = 0;
@@ -182,21 +188,22 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
         mbar_wait(&tmem_full_bar[acc], acc_phase, kTagEpiTmemFull, acc);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::BN;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::BN +
+                               group * (Cfg::CHUNKS_PER_GROUP * 32);
 #pragma unroll 1
-        for (int c = 0; c < Cfg::BN / 32; ++c) {
+        for (int c = 0; c < Cfg::CHUNKS_PER_GROUP; ++c) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + c * 32, v);  // includes tcgen05.wait::ld
-          if (c == Cfg::BN / 32 - 1) {
-            // the whole accumulator stage is now in registers: hand it back to the MMA warp
+          if (c == Cfg::CHUNKS_PER_GROUP - 1) {
+            // this thread's share of the accumulator stage is in registers: hand it back to the MMA warp
             tc_fence_before();
             if (CG == 1 || leader) mbar_arrive(&tmem_empty_bar[acc]);
             else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
           }
-          epi.chunk(ep, row, t * Cfg::BN + c * 32, v);
+          epi.chunk(ep, row, t * Cfg::BN + (group * Cfg::CHUNKS_PER_GROUP + c) * 32, v);
         }
       }
-      epi.end_unit(ep, row, m, s);
+      epi.end_unit(ep, row, m, s * Cfg::EPI_GROUPS + group);
     }
   }
 

@@ -20,11 +20,11 @@ static constexpr float kLn2 = 0.6931471805599453f;
 // Per (row, split): running max m and l = sum 2^(y - m) over the split's columns (log2 domain).
 struct LseEpilogue {
   struct Params {
-    float2* part;     // [rows_a][num_splits]  (m, l)
+    float2* part;     // [rows_a][num_slots]  (m, l)
     float* pos;       // [rows_a] positive logit (natural units, S * inv_T), or nullptr
     int rows_a;
     int rows_b;
-    int num_splits;
+    int num_slots;
     int half;         // N: pos(i) = (i + N) mod 2N; 0 = no positive / no diagonal mask (queue operand)
     float scale_log2; // inv_T * log2(e)
     float inv_t;
@@ -61,8 +61,8 @@ struct LseEpilogue {
     l = l * exp2f(m - m_new) + acc;
     m = m_new;
   }
-  __device__ __forceinline__ void end_unit(const Params& p, int row, int, int split) {
-    if (row < p.rows_a) p.part[static_cast<size_t>(row) * p.num_splits + split] = make_float2(m, l);
+  __device__ __forceinline__ void end_unit(const Params& p, int row, int, int slot) {
+    if (row < p.rows_a) p.part[static_cast<size_t>(row) * p.num_slots + slot] = make_float2(m, l);
   }
 };
 

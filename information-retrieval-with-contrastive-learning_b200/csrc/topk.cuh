@@ -23,32 +23,48 @@ __device__ __forceinline__ uint64_t make_key(float score, uint32_t idx) {
 __device__ __forceinline__ float key_score(uint64_t key) { return ordered_to_float(static_cast<uint32_t>(key >> 32)); }
 __device__ __forceinline__ uint32_t key_index(uint64_t key) { return ~static_cast<uint32_t>(key); }
 
-// Sorted (descending) list of the KCAP best keys seen so far, kept in registers: every loop is
-// fully unrolled so there is no dynamic register indexing.  `thr` caches the score of the worst
-// kept key: a candidate whose index is larger than every index seen so far (true for a scan in
-// increasing index order) can only enter if score > thr, which is the one compare on the fast path.
+// Sorted (descending) list of the KCAP best (score, index) pairs seen so far by ONE thread, kept
+// in registers: every loop is fully unrolled (no dynamic register indexing) and the insert is a
+// set of INDEPENDENT compare/selects (position j takes the old j-1, the new value, or stays), so
+// it issues at full rate instead of running a serial bubble chain.
+// The scan feeds candidates in increasing index order, so a new candidate that ties an existing
+// score has the larger index and belongs AFTER it: a strict `>` on the score alone implements
+// the (score desc, index asc) order.  `thr` caches the k-th best score (k <= KCAP, runtime): the
+// single compare on the fast path.  Empty slots are (-inf, 0xFFFFFFFF); NaN never enters.
 template <int KCAP>
 struct TopKList {
-  uint64_t keys[KCAP];
+  float sc[KCAP];
+  uint32_t ix[KCAP];
   float thr;
 
   __device__ __forceinline__ void reset() {
 #pragma unroll
-    for (int j = 0; j < KCAP; ++j) keys[j] = 0ull;
+    for (int j = 0; j < KCAP; ++j) {
+      sc[j] = -INFINITY;
+      ix[j] = 0xFFFFFFFFu;
+    }
     thr = -INFINITY;
   }
-  // bubble the key down from the top; a zero/smaller key passes through without change
-  __device__ __forceinline__ void insert_key(uint64_t key) {
+  // `s` = -inf makes this a no-op, which is how lanes without a candidate ride along
+  __device__ __forceinline__ void insert(float s, uint32_t idx, int k) {
+    bool gt[KCAP];
 #pragma unroll
-    for (int j = 0; j < KCAP; ++j) {
-      const uint64_t cur = keys[j];
-      const bool gt = key > cur;
-      keys[j] = gt ? key : cur;
-      key = gt ? cur : key;
+    for (int j = 0; j < KCAP; ++j) gt[j] = s > sc[j];
+#pragma unroll
+    for (int j = KCAP - 1; j >= 1; --j) {
+      sc[j] = gt[j] ? (gt[j - 1] ? sc[j - 1] : s) : sc[j];
+      ix[j] = gt[j] ? (gt[j - 1] ? ix[j - 1] : idx) : ix[j];
     }
-    thr = keys[KCAP - 1] == 0ull ? -INFINITY : key_score(keys[KCAP - 1]);
+    sc[0] = gt[0] ? s : sc[0];
+    ix[0] = gt[0] ? idx : ix[0];
+    float t = sc[0];
+#pragma unroll
+    for (int j = 1; j < KCAP; ++j) t = (j < k) ? sc[j] : t;
+    thr = t;  // sc[k-1]
   }
-  __device__ __forceinline__ void insert(float score, uint32_t idx) { insert_key(make_key(score, idx)); }
+  __device__ __forceinline__ uint64_t key(int j) const {
+    return sc[j] == -INFINITY ? 0ull : make_key(sc[j], ix[j]);
+  }
 };
 
 }  // namespace drs

@@ -38,10 +38,10 @@ def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
 def _check_matrix(name: str, t: torch.Tensor):
     if not isinstance(t, torch.Tensor) or t.dim() != 2:
         raise ValueError(f"{name} must be a 2-D tensor, got {type(t).__name__} with shape {getattr(t, 'shape', None)}")
-    if not t.is_cuda:
-        raise RuntimeError(f"{name} must live on a CUDA device: drs_b200 has no CPU path")
     if t.dtype not in _DTYPES:
         raise TypeError(f"{name} must be float32 or bfloat16, got {t.dtype}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device: drs_b200 has no CPU path")
 
 
 def search(queries: torch.Tensor, corpus: torch.Tensor, k: int, *, id_base: int = 0):
@@ -214,8 +214,10 @@ def all_gather_topk(slot_s: torch.Tensor, slot_i: torch.Tensor, group=None):
     global ids; returns the stacked [world, nq, k] tensors (same on every rank)."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    all_s = torch.empty((world,) + tuple(slot_s.shape), dtype=slot_s.dtype, device=slot_s.device)
-    all_i = torch.empty((world,) + tuple(slot_i.shape), dtype=slot_i.dtype, device=slot_i.device)
+    nq, k = slot_s.shape
+    # rank-major concatenation along dim 0 (the layout every backend accepts), viewed as [world, nq, k]
+    all_s = torch.empty(world * nq, k, dtype=slot_s.dtype, device=slot_s.device)
+    all_i = torch.empty(world * nq, k, dtype=slot_i.dtype, device=slot_i.device)
     dist.all_gather_into_tensor(all_s, slot_s.contiguous(), group=group)
     dist.all_gather_into_tensor(all_i, slot_i.contiguous(), group=group)
-    return all_s, all_i
+    return all_s.view(world, nq, k), all_i.view(world, nq, k)

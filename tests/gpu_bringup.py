@@ -132,7 +132,10 @@ CASES = {
     "nce_bf16_cg2_queue": lambda: _infonce_case("bf16", 2, 256, 128, 1024),
     "bench_cg1_10k_1m": lambda: _bench_case(1, 10000, 1000000, 768, 10),
     "bench_cg2_10k_1m": lambda: _bench_case(2, 10000, 1000000, 768, 10),
+    "bench_cg2_10k_5m": lambda: _bench_case(2, 10000, 5400000, 768, 10),
+    "bench_cg2_10k_25m": lambda: _bench_case(2, 10000, 25000000, 768, 10, iters=2),
     "bench_cg1_128_5m": lambda: _bench_case(1, 128, 5400000, 768, 10),
+    "bench_cg1_16_5m": lambda: _bench_case(1, 16, 5400000, 768, 10),
     "bench_cg2_256_5m": lambda: _bench_case(2, 256, 5400000, 768, 10),
 }
 
