@@ -51,6 +51,7 @@ struct Options {
   int num_ctas = 0;
   int splits = 0;
   int infonce_cta_group = 0;
+  int debug_flags = 0;
 } g_opt;
 
 struct DeviceInfo {
@@ -132,6 +133,7 @@ drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int 
   s.tiles_per_split = (s.total_b_tiles + splits - 1) / splits;
   s.num_splits = (s.total_b_tiles + s.tiles_per_split - 1) / s.tiles_per_split;  // no empty split
   s.col_groups = col_groups;
+  s.debug_flags = g_opt.debug_flags;
   return s;
 }
 
@@ -275,6 +277,7 @@ int drs_set_option(const char* name, int value) {
   else if (!strcmp(name, "search.num_ctas")) g_opt.num_ctas = value;
   else if (!strcmp(name, "search.splits")) g_opt.splits = value;
   else if (!strcmp(name, "infonce.cta_group")) g_opt.infonce_cta_group = value;
+  else if (!strcmp(name, "debug.flags")) g_opt.debug_flags = value;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;
 }
@@ -284,6 +287,7 @@ int drs_get_option(const char* name, int* value) {
   else if (!strcmp(name, "search.num_ctas")) *value = g_opt.num_ctas;
   else if (!strcmp(name, "search.splits")) *value = g_opt.splits;
   else if (!strcmp(name, "infonce.cta_group")) *value = g_opt.infonce_cta_group;
+  else if (!strcmp(name, "debug.flags")) *value = g_opt.debug_flags;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;
 }

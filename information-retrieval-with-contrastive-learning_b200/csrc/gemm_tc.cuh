@@ -33,6 +33,7 @@ struct GemmShape {
   int tiles_per_split;  // 256-row B tiles per split
   int total_b_tiles;    // ceil(rows_b / 256)
   int col_groups;       // epilogue threads per A row (each owns a column group of every tile)
+  int debug_flags;      // tuning instrumentation: 1 skip epilogue functor, 2 skip TMEM loads, 4 skip MMA issue
 };
 
 template <int CG>
@@ -159,10 +160,12 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             tc_fence_after();
             const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::A_BYTES));
             const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::B_BYTES));
+            if (!(shp.debug_flags & 4)) {
 #pragma unroll
-            for (int k = 0; k < Cfg::BK / 16; ++k) {
-              // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: start address field += 2
-              umma_bf16<CG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < Cfg::BK / 16; ++k) {
+                // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: start address field += 2
+                umma_bf16<CG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
             }
             umma_commit<CG>(&empty_bar[stage]);                       // smem slot free once these MMAs retire
             if (kb == nkb - 1) umma_commit<CG>(&tmem_full_bar[acc]);  // accumulator complete
@@ -193,14 +196,19 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll 1
         for (int c = 0; c < Cfg::CHUNKS_PER_GROUP; ++c) {
           uint32_t v[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, v);  // includes tcgen05.wait::ld
+          if (!(shp.debug_flags & 2)) {
+            tmem_ld_32x32b_x32(taddr + c * 32, v);  // includes tcgen05.wait::ld
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
           if (c == Cfg::CHUNKS_PER_GROUP - 1) {
             // this thread's share of the accumulator stage is in registers: hand it back to the MMA warp
             tc_fence_before();
             if (CG == 1 || leader) mbar_arrive(&tmem_empty_bar[acc]);
             else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
           }
-          epi.chunk(ep, row, t * Cfg::BN + (group * Cfg::CHUNKS_PER_GROUP + c) * 32, v);
+          if (!(shp.debug_flags & 1)) epi.chunk(ep, row, t * Cfg::BN + (group * Cfg::CHUNKS_PER_GROUP + c) * 32, v);
         }
       }
       epi.end_unit(ep, row, m, s * Cfg::EPI_GROUPS + group);

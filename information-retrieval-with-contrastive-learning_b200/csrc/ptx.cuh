@@ -65,12 +65,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// arrive on the barrier at the same smem offset in CTA `cta` of this cluster
+// Arrive on the barrier at the same smem offset in CTA `cta` of this cluster.  Deliberately the
+// plain form (default .release.cta): the .release.cluster form compiles to MEMBAR.ALL.GPU + error
+// barriers in front of every arrive, which serialises the producer.  No generic-proxy data is
+// published by these arrivals (TMA bytes are tracked by complete_tx, TMEM reads are ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync), so the cheap form is sufficient.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
 }

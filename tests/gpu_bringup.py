@@ -141,7 +141,7 @@ CASES = {
 
 
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] in CASES:
+    if len(sys.argv) == 2 and sys.argv[1] in CASES:
         try:
             res = CASES[sys.argv[1]]()
         except Exception as e:  # noqa: BLE001
