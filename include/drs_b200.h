@@ -59,6 +59,14 @@ int drs_search(const void* queries, int64_t nq, const void* corpus, int64_t nc, 
                int64_t id_base, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
                void* stream);
 
+/* The two phases of drs_search, separately launchable (drs_search == scan then select on the same
+ * stream): `scan` is the fused score GEMM + per-row running top-k that leaves the per-split
+ * candidate keys in the workspace; `select` reduces them to the final k.  Same arguments. */
+int drs_search_scan(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,
+                    void* workspace, size_t workspace_bytes, void* stream);
+int drs_search_select(const void* workspace, int64_t nq, int64_t nc, int dim, int dtype, int k, int64_t id_base,
+                      float* out_scores, int64_t* out_ids, void* stream);
+
 /*
  * Merge the per-shard top-k lists of a row-sharded corpus (after the all-gather):
  *   scores device [num_shards, nq, k], ids device [num_shards, nq, k] (id < 0 = empty slot)

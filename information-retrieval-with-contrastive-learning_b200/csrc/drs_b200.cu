@@ -300,30 +300,42 @@ int drs_search_workspace_bytes(int64_t nq, int64_t nc, int dim, int k, int dtype
   return DRS_OK;
 }
 
-int drs_search(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,
-               int64_t id_base, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
-               void* stream) {
-  if (!queries || !corpus || !out_scores || !out_ids) return fail(DRS_ERR_INVALID, "null pointer argument");
+int drs_search_scan(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  if (!queries || !corpus) return fail(DRS_ERR_INVALID, "null pointer argument");
   SearchPlan p;
   if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
   if (!workspace || workspace_bytes < p.ws_bytes)
     return fail(DRS_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", p.ws_bytes, workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint64_t* ws = static_cast<uint64_t*>(workspace);
-  int rc = DRS_OK;
   if (dtype == DRS_BF16) {
     if ((reinterpret_cast<uintptr_t>(queries) & 15) || (reinterpret_cast<uintptr_t>(corpus) & 15))
       return fail(DRS_ERR_INVALID, "bf16 path: queries and corpus must be 16-byte aligned");
-    if (p.cg == 1) rc = p.kcap == 16 ? launch_search_tc<1, 16>(p, queries, corpus, dim, ws, st)
-                                     : launch_search_tc<1, 32>(p, queries, corpus, dim, ws, st);
-    else           rc = p.kcap == 16 ? launch_search_tc<2, 16>(p, queries, corpus, dim, ws, st)
-                                     : launch_search_tc<2, 32>(p, queries, corpus, dim, ws, st);
-  } else {
-    rc = p.kcap == 16 ? launch_search_f32<16>(p, queries, corpus, dim, ws, st)
-                      : launch_search_f32<32>(p, queries, corpus, dim, ws, st);
+    if (p.cg == 1) return p.kcap == 16 ? launch_search_tc<1, 16>(p, queries, corpus, dim, ws, st)
+                                       : launch_search_tc<1, 32>(p, queries, corpus, dim, ws, st);
+    return p.kcap == 16 ? launch_search_tc<2, 16>(p, queries, corpus, dim, ws, st)
+                        : launch_search_tc<2, 32>(p, queries, corpus, dim, ws, st);
   }
-  if (rc) return rc;
-  return launch_merge_keys(ws, nq, num_slots(p.shape) * p.kcap, k, id_base, out_scores, out_ids, st);
+  return p.kcap == 16 ? launch_search_f32<16>(p, queries, corpus, dim, ws, st)
+                      : launch_search_f32<32>(p, queries, corpus, dim, ws, st);
+}
+
+int drs_search_select(const void* workspace, int64_t nq, int64_t nc, int dim, int dtype, int k, int64_t id_base,
+                      float* out_scores, int64_t* out_ids, void* stream) {
+  if (!workspace || !out_scores || !out_ids) return fail(DRS_ERR_INVALID, "null pointer argument");
+  SearchPlan p;
+  if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
+  return launch_merge_keys(static_cast<const uint64_t*>(workspace), nq, num_slots(p.shape) * p.kcap, k, id_base,
+                           out_scores, out_ids, static_cast<cudaStream_t>(stream));
+}
+
+int drs_search(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,
+               int64_t id_base, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+               void* stream) {
+  if (!out_scores || !out_ids) return fail(DRS_ERR_INVALID, "null pointer argument");
+  if (int rc = drs_search_scan(queries, nq, corpus, nc, dim, dtype, k, workspace, workspace_bytes, stream)) return rc;
+  return drs_search_select(workspace, nq, nc, dim, dtype, k, id_base, out_scores, out_ids, stream);
 }
 
 int drs_merge_shards(const float* scores, const int64_t* ids, int num_shards, int64_t nq, int k, float* out_scores,

@@ -44,7 +44,7 @@ def _check_matrix(name: str, t: torch.Tensor):
         raise RuntimeError(f"{name} must live on a CUDA device: drs_b200 has no CPU path")
 
 
-def search(queries: torch.Tensor, corpus: torch.Tensor, k: int, *, id_base: int = 0):
+def search(queries: torch.Tensor, corpus: torch.Tensor, k: int, *, id_base: int = 0, profile: Optional[list] = None):
     """Top-k corpus rows per query by dot product.
 
     queries [nq, D], corpus [Nc, D]: CUDA, row-major, same dtype (bf16 -> tcgen05 path, scores
@@ -55,6 +55,9 @@ def search(queries: torch.Tensor, corpus: torch.Tensor, k: int, *, id_base: int 
     Returns (scores fp32 [nq, k'], ids int64 [nq, k']) with k' = min(k, Nc) (like closest_docs,
     tfidf_doc_ranker.py:67-68, fewer rows than k returns them all), sorted by score descending,
     ties broken by the lower row index; ids = row index + id_base.
+
+    ``profile``: optional list; a (start, end) pair of CUDA events bracketing the scan kernel (the
+    fused score GEMM + top-k) on the current stream is appended to it, for roofline measurement.
     """
     _check_matrix("queries", queries)
     _check_matrix("corpus", corpus)
@@ -85,8 +88,18 @@ def search(queries: torch.Tensor, corpus: torch.Tensor, k: int, *, id_base: int 
         scores = torch.empty(nq, kk, dtype=torch.float32, device=dev)
         ids = torch.empty(nq, kk, dtype=torch.int64, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(lib.drs_search(queries.data_ptr(), nq, corpus.data_ptr(), nc, dim, dt, kk, int(id_base),
-                                  scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        if profile is None:
+            _lib.check(lib.drs_search(queries.data_ptr(), nq, corpus.data_ptr(), nc, dim, dt, kk, int(id_base),
+                                      scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        else:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            _lib.check(lib.drs_search_scan(queries.data_ptr(), nq, corpus.data_ptr(), nc, dim, dt, kk,
+                                           ws.data_ptr(), ws.numel(), stream))
+            ev1.record()
+            _lib.check(lib.drs_search_select(ws.data_ptr(), nq, nc, dim, dt, kk, int(id_base), scores.data_ptr(),
+                                             ids.data_ptr(), stream))
+            profile.append((ev0, ev1))
     return scores, ids
 
 
@@ -147,10 +160,10 @@ class DenseIndex:
     def get_doc_id(self, doc_index):
         return self.doc_dict[1][doc_index] if self.doc_dict else int(doc_index)
 
-    def search(self, queries: torch.Tensor, k: int = 1):
+    def search(self, queries: torch.Tensor, k: int = 1, profile: Optional[list] = None):
         """queries [nq, D] on any device (host tensors are copied in) -> device (scores, ids)."""
         q = queries.to(device=self.device, dtype=self.embeddings.dtype, non_blocking=True)
-        return search(q, self.embeddings, k, id_base=self.id_base)
+        return search(q, self.embeddings, k, id_base=self.id_base, profile=profile)
 
     def closest_docs(self, query: torch.Tensor, k: int = 1):
         """tfidf_doc_ranker.py:60-75 -- one query vector [D] -> (list of doc ids, np.ndarray scores)."""
@@ -192,9 +205,10 @@ class ShardedDenseIndex:
         self.total_rows = total_rows
         self.local = DenseIndex(local_embeddings, device=device, dtype=dtype, id_base=lo)
 
-    def search(self, queries: torch.Tensor, k: int = 1):
+    def search(self, queries: torch.Tensor, k: int = 1, profile: Optional[list] = None):
         kk = min(int(k), self.total_rows)
-        s, i = self.local.search(queries, min(kk, max(self.local.num_docs, 1))) if self.local.num_docs else (None, None)
+        s, i = (self.local.search(queries, min(kk, max(self.local.num_docs, 1)), profile=profile)
+                if self.local.num_docs else (None, None))
         nq = queries.shape[0]
         dev = self.local.device
         # fixed-size slots so every rank contributes the same number of bytes

@@ -1,0 +1,214 @@
+"""Parity of the CUDA search path (through the C ABI) against the CPU oracle.  GPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import drs_b200
+from oracle import dense_topk
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DEV = "cuda:0"
+
+
+def _unit(x):
+    return torch.nn.functional.normalize(x, dim=1)
+
+
+def _data(nq, nc, dim, dtype, planted=True, seed=1337):
+    g = torch.Generator(device=DEV).manual_seed(seed)               # main.py:45 default seed
+    c = _unit(torch.randn(nc, dim, generator=g, device=DEV))
+    if planted:
+        j = torch.randint(0, nc, (nq,), generator=g, device=DEV)
+        q = _unit(c[j] + 0.1 * torch.randn(nq, dim, generator=g, device=DEV))
+    else:
+        q = _unit(torch.randn(nq, dim, generator=g, device=DEV))
+    return q.to(dtype), c.to(dtype)
+
+
+def _check(q, c, k, s, i, score_rtol, gap):
+    """scores within tolerance; ids bit-exact wherever the oracle's score gap exceeds `gap`
+    (north star: 'top-k ids bit-exact wherever the score gap exceeds the tolerance')."""
+    rv, ri = dense_topk.search(q.cpu(), c.cpu(), k)
+    s, i = s.cpu(), i.cpu()
+    assert s.shape == rv.shape and i.shape == ri.shape and i.dtype == torch.int64 and s.dtype == torch.float32
+    torch.testing.assert_close(s, rv, rtol=score_rtol, atol=score_rtol * 1e-1)
+    assert torch.all(s[:, :-1] >= s[:, 1:]), "scores must be sorted descending"
+    kk = rv.shape[1]
+    v2, _ = dense_topk.search(q.cpu(), c.cpu(), kk + 1)          # one more, to know the gap below the k-th
+    if v2.shape[1] == kk + 1:
+        nxt = v2[:, 1:]
+    else:
+        nxt = torch.cat([rv[:, 1:], torch.full((rv.shape[0], 1), -1e30)], dim=1)
+    prev = torch.cat([torch.full((rv.shape[0], 1), 1e30), rv[:, :-1]], dim=1)
+    strict = ((rv - nxt) > gap) & ((prev - rv) > gap)
+    assert torch.equal(i[strict], ri[strict]), f"{(i[strict] != ri[strict]).sum().item()} ids differ outside ties"
+    return ri
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("nq,nc,dim,k", [(128, 256, 64, 5), (300, 20000, 768, 10), (77, 12345, 200, 10),
+                                         (1, 1000, 128, 1), (513, 70000, 128, 16), (64, 9000, 768, 32)])
+def test_bf16_tcgen05_parity(cg, nq, nc, dim, k):
+    q, c = _data(nq, nc, dim, torch.bfloat16, planted=(nq % 2 == 0))
+    drs_b200.set_option("search.cta_group", cg)
+    try:
+        s, i = drs_b200.search(q, c, k)
+    finally:
+        drs_b200.set_option("search.cta_group", 0)
+    # bf16 path tolerance from the north star: 2e-2 relative.  The oracle consumes the SAME bf16
+    # values upcast to fp32, so the observed error is fp32 summation order only.
+    _check(q, c, k, s, i, score_rtol=2e-2, gap=1e-4)
+
+
+@pytest.mark.parametrize("nq,nc,dim,k", [(100, 5000, 64, 5), (77, 1234, 100, 10), (1000, 100000, 768, 5),
+                                         (3, 40, 7, 4), (130, 3000, 33, 32)])
+def test_fp32_exact_parity(nq, nc, dim, k):
+    """BASELINE config 0 (1k claims x 100k x 768 fp32, top-5) and ragged shapes; 1e-5 relative."""
+    q, c = _data(nq, nc, dim, torch.float32, planted=(dim != 7))
+    s, i = drs_b200.search(q, c, k)
+    _check(q, c, k, s, i, score_rtol=1e-5, gap=2e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ties_break_to_lower_index(dtype):
+    """Exact duplicates of a corpus row: equal scores, ids must come out in ascending order,
+    across tiles, CTAs and splits."""
+    g = torch.Generator(device=DEV).manual_seed(7)
+    c = _unit(torch.randn(30000, 64, generator=g, device=DEV)).to(dtype)
+    dup = [5, 300, 4097, 12288, 29999]
+    for d in dup[1:]:
+        c[d] = c[dup[0]]
+    q = c[dup[0]].float().repeat(4, 1).to(dtype)
+    s, i = drs_b200.search(q, c, 8)
+    assert i[:, :5].cpu().tolist() == [dup] * 4
+    assert torch.all(s[:, :5] == s[:, :1])
+    rv, ri = dense_topk.search(q.cpu(), c.cpu(), 8)
+    assert torch.equal(i[:, :5].cpu(), ri[:, :5])
+
+
+def test_k_larger_than_corpus_and_tiny_corpus():
+    q, c = _data(9, 6, 64, torch.bfloat16, planted=False)
+    s, i = drs_b200.search(q, c, 10)                              # closest_docs :67-68 -> all 6 rows
+    assert s.shape == (9, 6)
+    rv, ri = dense_topk.search(q.cpu(), c.cpu(), 10)
+    assert torch.equal(i.cpu(), ri)
+    assert sorted(i[0].cpu().tolist()) == list(range(6))
+
+
+def test_id_base_and_sharded_merge_equals_single_search():
+    """SURVEY 8(e) on one GPU: shard the corpus, search each shard with its global offset, merge
+    with the engine's merge kernel -> identical to the unsharded search and to the oracle."""
+    q, c = _data(200, 50001, 128, torch.bfloat16)
+    s_full, i_full = drs_b200.search(q, c, 10)
+    for world in (2, 3, 8):
+        ss, ii = [], []
+        for r in range(world):
+            lo, hi = drs_b200.shard_bounds(c.shape[0], r, world)
+            s, i = drs_b200.search(q, c[lo:hi], 10, id_base=lo)
+            ss.append(s)
+            ii.append(i)
+        ms, mi = drs_b200.merge_shards(torch.stack(ss), torch.stack(ii))
+        assert torch.equal(mi, i_full) and torch.equal(ms, s_full)
+    rv, ri = dense_topk.sharded_search(q.cpu(), c.cpu(), 10, 4)
+    assert torch.equal(i_full.cpu()[:, 0], ri[:, 0])
+
+
+def test_merge_shards_with_empty_slots_and_cross_shard_ties():
+    s = torch.tensor([[[0.9, 0.5, float("-inf")]], [[0.9, 0.9, 0.1]]], device=DEV)      # [2 shards, 1 query, 3]
+    i = torch.tensor([[[10, 11, -1]], [[3, 40, 41]]], device=DEV)
+    ms, mi = drs_b200.merge_shards(s, i)
+    assert mi.cpu().tolist() == [[3, 10, 40]]
+    assert ms.cpu().tolist() == [[pytest.approx(0.9)] * 3]
+    s = torch.full((2, 1, 3), float("-inf"), device=DEV)
+    i = torch.full((2, 1, 3), -1, dtype=torch.int64, device=DEV)
+    s[1, 0, 0], i[1, 0, 0] = 0.25, 77
+    ms, mi = drs_b200.merge_shards(s, i)
+    assert mi.cpu().tolist() == [[77, -1, -1]]
+
+
+def test_dense_index_mirrors_closest_docs():
+    """TfidfDocRanker surface (tfidf_doc_ranker.py:52-84): (list of doc ids, f64 ndarray of scores)."""
+    q, c = _data(5, 3000, 64, torch.float32)
+    names = [f"doc_{n}" for n in range(c.shape[0])]
+    index = drs_b200.DenseIndex(c, names, dtype=torch.float32)
+    ids, scores = index.closest_docs(q[0].cpu(), k=5)              # host query vector is copied in
+    rv, ri = dense_topk.search(q[:1].cpu(), c.cpu(), 5)
+    assert ids == [names[j] for j in ri[0].tolist()]
+    assert isinstance(scores, np.ndarray) and scores.dtype == np.float64
+    np.testing.assert_allclose(scores, rv[0].numpy(), rtol=1e-5)
+    batch = index.batch_closest_docs(q, k=3, num_workers=4)
+    assert len(batch) == 5 and batch[0][0] == ids[:3]
+    assert index.get_doc_index("doc_17") == 17 and index.get_doc_id(17) == "doc_17"
+
+
+def test_closest_docs_golden_through_the_engine():
+    """The reference's own closest_docs outputs (golden, dyadic values so fp32 is exact):
+    dense restatement = query row x doc_mat columns, fp32 exact path."""
+    z = np.load(os.path.join(GOLDEN, "closest_docs.npz"))
+    corpus = torch.from_numpy(z["doc_mat"].T.copy()).float().to(DEV)          # [docs, hash]
+    for qv, k, ids, scs in zip(z["queries"], z["k"], z["ids"], z["scores"]):
+        n_ret = int((ids >= 0).sum())
+        kk = min(int(k), 32, n_ret)
+        s, i = drs_b200.search(torch.from_numpy(qv[None, :]).float().to(DEV), corpus, kk)
+        np.testing.assert_array_equal(s[0].cpu().numpy().astype(np.float64), scs[:kk])   # scores identical
+        full = qv @ z["doc_mat"]
+        np.testing.assert_array_equal(full[i[0].cpu().numpy()], scs[:kk])                 # ids carry those scores
+        same = np.diff(scs[:kk]) == 0
+        assert np.all(np.diff(i[0].cpu().numpy())[same] > 0)                              # ties -> lower index first
+
+
+def test_unsupported_arguments_raise_runtime_error():
+    q, c = _data(4, 100, 64, torch.bfloat16)
+    with pytest.raises(RuntimeError, match="exceeds the engine limit"):
+        drs_b200.search(q, c, 64)
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        drs_b200.search(q[:, :60].contiguous(), c[:, :60].contiguous(), 3)
+
+
+@pytest.mark.parametrize("nq", [16, 128])
+def test_small_batch_bandwidth_regime_parity(nq):
+    """BASELINE rows 2b/3b: few claims per corpus pass (HBM-bound regime), 1M rows."""
+    q, c = _data(nq, 1_000_000, 768, torch.bfloat16)
+    s, i = drs_b200.search(q, c, 10)
+    _check(q, c, 10, s, i, score_rtol=2e-2, gap=1e-4)
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 1 at full size (10k claims x 5.4M x 768 bf16, top-10): size-independent
+    properties instead of an oracle pass -- planted neighbours are found first, rows are sorted,
+    ids are unique and in range, returned scores match a recomputation of those exact pairs, and
+    sharding + merge is idempotent with the single pass."""
+    nq, nc, dim, k = 10000, 5_400_000, 768, 10
+    g = torch.Generator(device=DEV).manual_seed(1337)
+    c = torch.empty(nc, dim, dtype=torch.bfloat16, device=DEV)
+    for r0 in range(0, nc, 1 << 20):
+        r1 = min(nc, r0 + (1 << 20))
+        c[r0:r1] = _unit(torch.randn(r1 - r0, dim, generator=g, device=DEV))
+    planted = torch.randint(0, nc, (nq,), generator=g, device=DEV)
+    q = _unit(c[planted].float() + 0.05 * torch.randn(nq, dim, generator=g, device=DEV)).bfloat16()
+    s, i = drs_b200.search(q, c, k)
+    assert torch.equal(i[:, 0], planted)
+    assert torch.all(s[:, :-1] >= s[:, 1:])
+    assert int(i.min()) >= 0 and int(i.max()) < nc
+    assert all(len(set(r)) == k for r in i[:256].cpu().tolist())
+    rec = (q.float()[:, None, :] * c[i.reshape(-1)].float().reshape(nq, k, dim)).sum(-1)
+    torch.testing.assert_close(s, rec, rtol=2e-2, atol=1e-4)
+    # a 512-claim slice against the oracle over a 200k-row window that contains each planted row's shard
+    win = c[:200000]
+    sub = (planted < 200000).nonzero().flatten()[:64]
+    if len(sub):
+        sv, si = drs_b200.search(q[sub], win, k)
+        rv, ri = dense_topk.search(q[sub].cpu(), win.cpu(), k)
+        assert torch.equal(si.cpu()[:, 0], ri[:, 0])
+        torch.testing.assert_close(sv.cpu(), rv, rtol=2e-2, atol=1e-4)
+    ss, ii = [], []
+    for r in range(4):
+        lo, hi = drs_b200.shard_bounds(nc, r, 4)
+        a, b = drs_b200.search(q, c[lo:hi], k, id_base=lo)
+        ss.append(a)
+        ii.append(b)
+    ms, mi = drs_b200.merge_shards(torch.stack(ss), torch.stack(ii))
+    assert torch.equal(mi, i) and torch.equal(ms, s)
