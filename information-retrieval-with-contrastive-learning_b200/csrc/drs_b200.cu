@@ -52,6 +52,9 @@ struct Options {
   int splits = 0;
   int infonce_cta_group = 0;
   int debug_flags = 0;
+  int b_hint = 0;
+  int stagger_cycles = 0;
+  int round_barrier = 1;
 } g_opt;
 
 struct DeviceInfo {
@@ -134,10 +137,14 @@ drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int 
   s.num_splits = (s.total_b_tiles + s.tiles_per_split - 1) / s.tiles_per_split;  // no empty split
   s.col_groups = col_groups;
   s.debug_flags = g_opt.debug_flags;
+  s.b_hint = g_opt.b_hint;
+  s.stagger_cycles = g_opt.stagger_cycles;
+  s.round_counter = nullptr;
   return s;
 }
 
 constexpr int kTcColGroups = drs::GemmCfg<1>::EPI_GROUPS;
+constexpr size_t kWsHeaderBytes = 256;  // round-barrier counter, zeroed before every scan
 inline int num_slots(const drs::GemmShape& s) { return s.num_splits * s.col_groups; }
 
 struct SearchPlan {
@@ -177,7 +184,7 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
   } else {
     return fail(DRS_ERR_INVALID, "unknown dtype %d", dtype);
   }
-  p->ws_bytes = static_cast<size_t>(nq) * num_slots(p->shape) * p->kcap * sizeof(uint64_t);
+  p->ws_bytes = kWsHeaderBytes + static_cast<size_t>(nq) * num_slots(p->shape) * p->kcap * sizeof(uint64_t);
   return DRS_OK;
 }
 
@@ -278,6 +285,9 @@ int drs_set_option(const char* name, int value) {
   else if (!strcmp(name, "search.splits")) g_opt.splits = value;
   else if (!strcmp(name, "infonce.cta_group")) g_opt.infonce_cta_group = value;
   else if (!strcmp(name, "debug.flags")) g_opt.debug_flags = value;
+  else if (!strcmp(name, "tune.b_hint")) g_opt.b_hint = value;
+  else if (!strcmp(name, "tune.stagger_cycles")) g_opt.stagger_cycles = value;
+  else if (!strcmp(name, "tune.round_barrier")) g_opt.round_barrier = value;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;
 }
@@ -288,6 +298,9 @@ int drs_get_option(const char* name, int* value) {
   else if (!strcmp(name, "search.splits")) *value = g_opt.splits;
   else if (!strcmp(name, "infonce.cta_group")) *value = g_opt.infonce_cta_group;
   else if (!strcmp(name, "debug.flags")) *value = g_opt.debug_flags;
+  else if (!strcmp(name, "tune.b_hint")) *value = g_opt.b_hint;
+  else if (!strcmp(name, "tune.stagger_cycles")) *value = g_opt.stagger_cycles;
+  else if (!strcmp(name, "tune.round_barrier")) *value = g_opt.round_barrier;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;
 }
@@ -308,10 +321,16 @@ int drs_search_scan(const void* queries, int64_t nq, const void* corpus, int64_t
   if (!workspace || workspace_bytes < p.ws_bytes)
     return fail(DRS_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", p.ws_bytes, workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  uint64_t* ws = static_cast<uint64_t*>(workspace);
+  uint64_t* ws = reinterpret_cast<uint64_t*>(static_cast<char*>(workspace) + kWsHeaderBytes);
   if (dtype == DRS_BF16) {
     if ((reinterpret_cast<uintptr_t>(queries) & 15) || (reinterpret_cast<uintptr_t>(corpus) & 15))
       return fail(DRS_ERR_INVALID, "bf16 path: queries and corpus must be 16-byte aligned");
+    DeviceInfo di;
+    if (int rc = get_device_info(&di)) return rc;
+    if (g_opt.round_barrier && p.grid <= di.num_sms) {   // all CTAs co-resident: the barrier cannot deadlock
+      DRS_CUDA(cudaMemsetAsync(workspace, 0, kWsHeaderBytes, st));
+      p.shape.round_counter = static_cast<unsigned int*>(workspace);
+    }
     if (p.cg == 1) return p.kcap == 16 ? launch_search_tc<1, 16>(p, queries, corpus, dim, ws, st)
                                        : launch_search_tc<1, 32>(p, queries, corpus, dim, ws, st);
     return p.kcap == 16 ? launch_search_tc<2, 16>(p, queries, corpus, dim, ws, st)
@@ -326,7 +345,8 @@ int drs_search_select(const void* workspace, int64_t nq, int64_t nc, int dim, in
   if (!workspace || !out_scores || !out_ids) return fail(DRS_ERR_INVALID, "null pointer argument");
   SearchPlan p;
   if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
-  return launch_merge_keys(static_cast<const uint64_t*>(workspace), nq, num_slots(p.shape) * p.kcap, k, id_base,
+  return launch_merge_keys(reinterpret_cast<const uint64_t*>(static_cast<const char*>(workspace) + kWsHeaderBytes), nq,
+                           num_slots(p.shape) * p.kcap, k, id_base,
                            out_scores, out_ids, static_cast<cudaStream_t>(stream));
 }
 

@@ -34,6 +34,9 @@ struct GemmShape {
   int total_b_tiles;    // ceil(rows_b / 256)
   int col_groups;       // epilogue threads per A row (each owns a column group of every tile)
   int debug_flags;      // tuning instrumentation: 1 skip epilogue functor, 2 skip TMEM loads, 4 skip MMA issue
+  int b_hint;           // L2 eviction hint for the B (corpus) tiles: 0 normal, 1 evict-first, 2 evict-last
+  int stagger_cycles;   // producer start delay per A-tile index (experiment knob)
+  unsigned int* round_counter;  // zeroed device counter for the per-round producer barrier, or nullptr
 };
 
 template <int CG>
@@ -56,7 +59,7 @@ struct GemmCfg {
 };
 
 // Tags reported by a timed-out mbarrier wait (see ptx.cuh)
-enum : uint32_t { kTagProducerEmpty = 1, kTagMmaFull = 2, kTagMmaTmemEmpty = 3, kTagEpiTmemFull = 4 };
+enum : uint32_t { kTagProducerEmpty = 1, kTagMmaFull = 2, kTagMmaTmemEmpty = 3, kTagEpiTmemFull = 4, kTagRoundBarrier = 5 };
 
 // Epi requirements:
 //   struct Params;                                        (trivially copyable, passed by value)
@@ -115,30 +118,53 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ------------------------------------------------------------ TMA producer (one thread)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int u = cluster; u < num_units; u += nclusters) {
-        const int m = u % shp.num_m_tiles, s = u / shp.num_m_tiles;
-        const int t0 = s * shp.tiles_per_split;
-        const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
-        const int row_a = (m * CG + static_cast<int>(cta_rank)) * Cfg::BM;
-        for (int t = t0; t < t1; ++t) {
-          const int row_b = t * Cfg::BN + static_cast<int>(cta_rank) * Cfg::BN_CTA;
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u, kTagProducerEmpty, stage);
-            void* dst_a = smem_a + stage * Cfg::A_BYTES;
-            void* dst_b = smem_b + stage * Cfg::B_BYTES;
-            if constexpr (CG == 1) {
-              mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-              tma_load_2d(dst_a, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
-              tma_load_2d(dst_b, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, kEvictNormal);
-            } else {
-              tma_load_2d_pair(dst_a, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
-              tma_load_2d_pair(dst_b, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, kEvictNormal);
-              if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-              else mbar_arrive_cluster(&full_bar[stage], 0);
-            }
-            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+      const uint64_t hint_b = shp.b_hint == 1 ? kEvictFirst : (shp.b_hint == 2 ? kEvictLast : kEvictNormal);
+      if (shp.stagger_cycles > 0) {
+        const long long until = clock64() + static_cast<long long>(shp.stagger_cycles) * (cluster % shp.num_m_tiles);
+        while (clock64() < until) {}
+      }
+      // Round barrier: every producer starts round r (its r-th unit) only after ALL producers have
+      // issued the loads of round r-1.  The clusters that share a B range then sweep it in lockstep
+      // and each B tile is fetched from HBM once per round instead of once per straggler (without
+      // it the groups drift apart by more than the L2 can hold and the corpus is re-read ~18x).
+      // All CTAs are co-resident (grid <= SM count, one CTA per SM), so the spin cannot deadlock.
+      const int num_rounds = (num_units + static_cast<int>(nclusters) - 1) / static_cast<int>(nclusters);
+      for (int round = 0; round < num_rounds; ++round) {
+        const int u = static_cast<int>(cluster) + round * static_cast<int>(nclusters);
+        if (shp.round_counter != nullptr && round > 0) {
+          const unsigned int target = static_cast<unsigned int>(round) * gridDim.x;
+          const long long t_start = clock64();
+          while (ld_acquire_gpu_u32(shp.round_counter) < target) {
+            __nanosleep(64);
+            if (clock64() - t_start > kMbarTimeoutCycles) mbar_hang(kTagRoundBarrier, round, target);
           }
         }
+        if (u < num_units) {
+          const int m = u % shp.num_m_tiles, s = u / shp.num_m_tiles;
+          const int t0 = s * shp.tiles_per_split;
+          const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
+          const int row_a = (m * CG + static_cast<int>(cta_rank)) * Cfg::BM;
+          for (int t = t0; t < t1; ++t) {
+            const int row_b = t * Cfg::BN + static_cast<int>(cta_rank) * Cfg::BN_CTA;
+            for (int kb = 0; kb < nkb; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u, kTagProducerEmpty, stage);
+              void* dst_a = smem_a + stage * Cfg::A_BYTES;
+              void* dst_b = smem_b + stage * Cfg::B_BYTES;
+              if constexpr (CG == 1) {
+                mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                tma_load_2d(dst_a, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
+                tma_load_2d(dst_b, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, hint_b);
+              } else {
+                tma_load_2d_pair(dst_a, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
+                tma_load_2d_pair(dst_b, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, hint_b);
+                if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                else mbar_arrive_cluster(&full_bar[stage], 0);
+              }
+              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+        if (shp.round_counter != nullptr) red_release_gpu_add_u32(shp.round_counter, 1u);
       }
     }
   } else if (warp == 1) {

@@ -69,8 +69,9 @@ def test_against_oracle_with_upstream_gradient(precision, n, dim, klen):
     tol, gtol = (1e-5, 1e-4) if precision == "fp32" else (2e-2, 3e-2)
     assert abs(loss.item() - rl.item()) <= tol * abs(rl.item()) + 1e-5
     scale = max(rdq.abs().max().item(), rdk.abs().max().item(), 1e-12) * 0.5
-    assert (dq.double() - 0.5 * rdq).abs().max().item() <= gtol * scale + 1e-7
-    assert (dk.double() - 0.5 * rdk).abs().max().item() <= gtol * scale + 1e-7
+    # absolute floor: with N == 1 the only logit is the positive, loss and gradients are exactly 0
+    assert (dq.double() - 0.5 * rdq).abs().max().item() <= gtol * scale + 1e-5
+    assert (dk.double() - 0.5 * rdk).abs().max().item() <= gtol * scale + 1e-5
 
 
 def test_config4_full_size_forward_backward():
