@@ -78,14 +78,18 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       "r"(cta)
       : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the
+// hint, in ns, expires) instead of re-issuing the poll every ~150 cycles.  Without the hint the
+// epilogue warps' polling was 43 % of all executed instructions (ncu source page) on a
+// power-capped part, i.e. clock taken from the tensor pipe.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(2000000u)
       : "memory");
   return ok != 0;
 }
