@@ -94,6 +94,36 @@ int drs_infonce_backward(const float* q, const float* k, const float* queue, int
                          float inv_temperature, int precision, const float* lse, const float* grad_loss, float* dq,
                          float* dk, void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * MoCo-form InfoNCE.  Replaces: InfoNCE.forward (src/contrastor/contrastive_loss.py:26-44):
+ * logits = [q.k | q @ queue] / T, label 0, CrossEntropyLoss with MEAN reduction.
+ *   q, k device [n, dim] fp32; queue device [dim, queue_len] fp32 (required; no gradient, :32)
+ *   loss device [1]; lse device [n] (saved for backward); dq, dk device [n, dim].
+ */
+int drs_moco_workspace_bytes(int64_t n, int dim, int64_t queue_len, int precision, size_t* bytes);
+int drs_moco_forward(const float* q, const float* k, const float* queue, int64_t n, int dim, int64_t queue_len,
+                     float inv_temperature, int precision, float* loss, float* lse, void* workspace,
+                     size_t workspace_bytes, void* stream);
+int drs_moco_backward(const float* q, const float* k, const float* queue, int64_t n, int dim, int64_t queue_len,
+                      float inv_temperature, int precision, const float* lse, const float* grad_loss, float* dq,
+                      float* dk, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * ProtoNCE, one cluster set.  Replaces the arithmetic of NCELoss._compute_proto_loss
+ * (src/contrastor/contrastive_loss.py:112-131) after the prototype selection (:99-110, host side):
+ *   protos device [num_protos, dim] fp32 = cat(pos_prototypes (n rows), neg_prototypes)  (:112)
+ *   inv_temps device [num_protos] fp32 = 1 / density of each selected prototype          (:122-124)
+ *   logits = q @ protos^T * inv_temps; label of row i is i (:118-119); loss[0] = CE SUM (:131).
+ * Backward: dq (+)= grad_loss[0] * dloss/dq  (accumulate != 0 adds into dq: sets are summed, :129-131).
+ */
+int drs_proto_workspace_bytes(int64_t n, int dim, int64_t num_protos, int precision, size_t* bytes);
+int drs_proto_forward(const float* q, const float* protos, const float* inv_temps, int64_t n, int dim,
+                      int64_t num_protos, int precision, float* loss, float* lse, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int drs_proto_backward(const float* q, const float* protos, const float* inv_temps, int64_t n, int dim,
+                       int64_t num_protos, int precision, const float* lse, const float* grad_loss, float* dq,
+                       int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,10 +13,10 @@ Everything computes in hand-written sm_100a CUDA behind the C ABI of include/drs
 """
 from . import _lib, build
 from ._lib import get_option, set_option
-from .loss import NCELoss, info_nce_loss
+from .loss import InfoNCE, NCELoss, info_nce_loss, proto_nce_loss
 from .retrieval import DenseIndex, ShardedDenseIndex, all_gather_topk, merge_shards, search, shard_bounds
 
 __all__ = [
     "search", "merge_shards", "DenseIndex", "ShardedDenseIndex", "all_gather_topk", "shard_bounds",
-    "NCELoss", "info_nce_loss", "set_option", "get_option", "build",
+    "NCELoss", "InfoNCE", "info_nce_loss", "proto_nce_loss", "set_option", "get_option", "build",
 ]

@@ -372,5 +372,6 @@ int drs_merge_shards(const float* scores, const int64_t* ids, int num_shards, in
 }
 
 #include "infonce_api.inc"
+#include "contrast_api.inc"
 
 }  // extern "C"

@@ -12,6 +12,7 @@ rounded to bf16, tcgen05 MMA, fp32 accumulate) or 'fp32' (FFMA path for exact co
 from __future__ import annotations
 
 import ctypes
+import random
 
 import torch
 
@@ -108,6 +109,137 @@ def info_nce_loss(q, k, queue=None, temperature=0.05, precision="auto"):
     return _InfoNceFunction.apply(q, k, queue, 1.0 / float(temperature), precision)
 
 
+class _MocoFunction(torch.autograd.Function):
+    """``InfoNCE.forward`` (contrastive_loss.py:26-44): logits = [q.k | q @ queue] / T, CE mean."""
+
+    @staticmethod
+    def forward(ctx, q, k, queue, inv_t, precision):
+        if not (q.is_cuda and k.is_cuda):
+            raise RuntimeError("drs_b200 InfoNCE needs CUDA tensors: there is no CPU path")
+        if q.shape != k.shape or q.dim() != 2:
+            raise ValueError(f"q and k must both be [N, D], got {tuple(q.shape)} and {tuple(k.shape)}")
+        qf = q.detach().contiguous().float()
+        kf = k.detach().contiguous().float()
+        n, dim = qf.shape
+        if queue is None or queue.dim() != 2 or queue.shape[0] != dim:
+            raise ValueError(f"queue must be [D, K] with D={dim}")
+        qu = queue.detach().to(device=q.device).contiguous().float()          # :32 queue.clone().detach()
+        klen = qu.shape[1]
+        prec = _pick_precision(precision, 4, dim, klen)                       # no batch-size constraint here
+        lib = _lib.load()
+        dev = q.device
+        with torch.cuda.device(dev):
+            need = ctypes.c_size_t(0)
+            _lib.check(lib.drs_moco_workspace_bytes(n, dim, klen, prec, ctypes.byref(need)))
+            ws = _workspace(dev, need.value)
+            loss = torch.empty(1, dtype=torch.float32, device=dev)
+            lse = torch.empty(n, dtype=torch.float32, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.drs_moco_forward(qf.data_ptr(), kf.data_ptr(), qu.data_ptr(), n, dim, klen, float(inv_t), prec,
+                                            loss.data_ptr(), lse.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        ctx.save_for_backward(qf, kf, qu, lse)
+        ctx.inv_t, ctx.prec, ctx.in_dtypes = float(inv_t), prec, (q.dtype, k.dtype)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        qf, kf, qu, lse = ctx.saved_tensors
+        n, dim = qf.shape
+        klen = qu.shape[1]
+        lib = _lib.load()
+        dev = qf.device
+        with torch.cuda.device(dev):
+            need = ctypes.c_size_t(0)
+            _lib.check(lib.drs_moco_workspace_bytes(n, dim, klen, ctx.prec, ctypes.byref(need)))
+            ws = _workspace(dev, need.value)
+            g = grad_out.detach().reshape(1).to(device=dev, dtype=torch.float32).contiguous()
+            dq, dk = torch.empty_like(qf), torch.empty_like(kf)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.drs_moco_backward(qf.data_ptr(), kf.data_ptr(), qu.data_ptr(), n, dim, klen, ctx.inv_t, ctx.prec,
+                                             lse.data_ptr(), g.data_ptr(), dq.data_ptr(), dk.data_ptr(), ws.data_ptr(),
+                                             ws.numel(), stream))
+        return dq.to(ctx.in_dtypes[0]), dk.to(ctx.in_dtypes[1]), None, None, None
+
+
+class InfoNCE(torch.nn.Module):
+    """contrastive_loss.py:20-44 (MoCo form).  ``forward(q, k, queue)``; mean-reduced CE, label 0."""
+
+    def __init__(self, loss_config):
+        super().__init__()
+        self.T = loss_config['temperature']                       # :23
+        self.precision = loss_config.get('precision', 'auto')
+
+    def forward(self, q, k, queue):
+        return _MocoFunction.apply(q, k, queue, 1.0 / float(self.T), self.precision)
+
+
+class _ProtoFunction(torch.autograd.Function):
+    """Sum over cluster sets of CE_sum(q @ protos_s^T / temps_s, label i) / num_sets
+    (contrastive_loss.py:112-134), prototypes already selected."""
+
+    @staticmethod
+    def forward(ctx, q, precision, *sets):
+        if not q.is_cuda:
+            raise RuntimeError("drs_b200 ProtoNCE needs CUDA tensors: there is no CPU path")
+        qf = q.detach().contiguous().float()
+        n, dim = qf.shape
+        dev = q.device
+        protos = [s.detach().to(device=dev).contiguous().float() for s in sets[0::2]]
+        inv_temps = [(1.0 / s.detach().to(device=dev).float()).contiguous() for s in sets[1::2]]
+        lib = _lib.load()
+        total = torch.zeros((), dtype=torch.float32, device=dev)
+        lses, precs = [], []
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            for pr, it in zip(protos, inv_temps):
+                p = pr.shape[0]
+                prec = _pick_precision(precision, 4, dim, p)
+                need = ctypes.c_size_t(0)
+                _lib.check(lib.drs_proto_workspace_bytes(n, dim, p, prec, ctypes.byref(need)))
+                ws = _workspace(dev, need.value)
+                loss = torch.empty(1, dtype=torch.float32, device=dev)
+                lse = torch.empty(n, dtype=torch.float32, device=dev)
+                _lib.check(lib.drs_proto_forward(qf.data_ptr(), pr.data_ptr(), it.data_ptr(), n, dim, p, prec,
+                                                 loss.data_ptr(), lse.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+                total = total + loss[0]
+                lses.append(lse)
+                precs.append(prec)
+        ctx.save_for_backward(qf, *protos, *inv_temps, *lses)
+        ctx.num_sets, ctx.precs, ctx.in_dtype = len(protos), precs, q.dtype
+        return total / len(protos)                                # :134
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        saved = ctx.saved_tensors
+        ns = ctx.num_sets
+        qf, protos, inv_temps, lses = saved[0], saved[1:1 + ns], saved[1 + ns:1 + 2 * ns], saved[1 + 2 * ns:]
+        n, dim = qf.shape
+        dev = qf.device
+        lib = _lib.load()
+        dq = torch.empty_like(qf)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            g = (grad_out.detach().reshape(1).to(device=dev, dtype=torch.float32) / ns).contiguous()
+            for s, (pr, it, lse) in enumerate(zip(protos, inv_temps, lses)):
+                p = pr.shape[0]
+                need = ctypes.c_size_t(0)
+                _lib.check(lib.drs_proto_workspace_bytes(n, dim, p, ctx.precs[s], ctypes.byref(need)))
+                ws = _workspace(dev, need.value)
+                _lib.check(lib.drs_proto_backward(qf.data_ptr(), pr.data_ptr(), it.data_ptr(), n, dim, p, ctx.precs[s],
+                                                  lse.data_ptr(), g.data_ptr(), dq.data_ptr(), 1 if s else 0,
+                                                  ws.data_ptr(), ws.numel(), stream))
+        return (dq.to(ctx.in_dtype), None) + (None,) * (2 * ns)
+
+
+def proto_nce_loss(q, protos, temps, precision="auto"):
+    """Functional ProtoNCE on selected prototypes: ``protos[s]`` is [N + r, D] with row i the positive
+    prototype of q[i], ``temps[s]`` the matching densities (contrastive_loss.py:112,:122-123)."""
+    flat = []
+    for pr, tp in zip(protos, temps):
+        flat += [pr, tp]
+    return _ProtoFunction.apply(q, precision, *flat)
+
+
 class NCELoss(torch.nn.Module):
     """contrastive_loss.py:47-141.  ``forward(q, k, queue, cluster_result=None, index=None)``."""
 
@@ -118,14 +250,32 @@ class NCELoss(torch.nn.Module):
         if 'cluster' in loss_config:                              # :52-54
             self.num_cluster = loss_config['cluster']['num_cluster']
             self.num_neg_proto = loss_config['cluster']['num_neg_proto']
+        self._rng = random.Random(1126)                           # the reference seeds `random` with 1126 (:4)
 
     def _compute_info_loss(self, q, k, queue=None):
         return info_nce_loss(q, k, queue, self.T, self.precision)
 
+    def select_prototypes(self, cluster_result, index):
+        """The host-side selection of contrastive_loss.py:99-112,:122-123: positive prototype of
+        each sample, ``num_neg_proto`` sampled negatives, and their densities.
+        ``random.sample(set, r)`` (:109) raises on Python >= 3.11, so the population is sorted
+        first (a set has no defined order anyway); everything else follows the reference,
+        including ``range(emb2cluster.max())`` (:105), which leaves the highest cluster id out."""
+        protos, temps = [], []
+        for emb2cluster, prototypes, density in zip(cluster_result['emb2cluster'], cluster_result['centroids'],
+                                                    cluster_result['density']):
+            pos_proto_id = emb2cluster[index.tolist()]                                   # :101
+            all_proto_id = range(int(emb2cluster.max()))                                 # :105
+            neg_proto_id = sorted(set(all_proto_id) - set(pos_proto_id.tolist()))        # :106
+            neg_proto_id = self._rng.sample(neg_proto_id, self.num_neg_proto)            # :109
+            ids = torch.cat([pos_proto_id.cpu().long(), torch.LongTensor(neg_proto_id)])
+            protos.append(prototypes[ids.to(prototypes.device)])                         # :102,:110,:112
+            temps.append(density[ids.to(density.device)])                                # :122-123
+        return protos, temps
+
     def _compute_proto_loss(self, q, cluster_result, index):
-        raise NotImplementedError(
-            "ProtoNCE (contrastive_loss.py:95-135) is a 'next' row of the hot-path scope (SURVEY.md 8f-2) "
-            "and is not built yet")
+        protos, temps = self.select_prototypes(cluster_result, index)
+        return proto_nce_loss(q, protos, temps, self.precision)   # :115-134
 
     def forward(self, q, k, queue, cluster_result=None, index=None):
         loss = self._compute_info_loss(q, k, queue)               # :138

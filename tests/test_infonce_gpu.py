@@ -98,5 +98,82 @@ def test_module_is_stateless_and_k_no_grad_ok():
     loss = crit(q, k, None)
     loss.backward()
     assert q.grad is not None and torch.isfinite(q.grad).all() and loss.device.type == "cuda" and loss.dim() == 0
-    with pytest.raises(NotImplementedError):
-        crit(q, k, None, cluster_result={"emb2cluster": []}, index=torch.arange(64))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "moco_*.npz"))))
+def test_moco_infonce_matches_reference_golden(path, precision):
+    """InfoNCE.forward (contrastive_loss.py:26-44) vs the reference's own outputs."""
+    z = np.load(path)
+    q = torch.from_numpy(z["q"]).to(DEV).requires_grad_(True)
+    k = torch.from_numpy(z["k"]).to(DEV).requires_grad_(True)
+    crit = drs_b200.InfoNCE({"temperature": float(z["temperature"]), "precision": precision})
+    loss = crit(q, k, torch.from_numpy(z["queue"]).to(DEV))
+    loss.backward()
+    tol, gtol = (1e-5, 1e-4) if precision == "fp32" else (2e-2, 3e-2)
+    assert abs(loss.item() - float(z["loss"])) <= tol * abs(float(z["loss"])) + 1e-6
+    scale = max(np.abs(z["dq"]).max(), np.abs(z["dk"]).max())
+    np.testing.assert_allclose(q.grad.cpu().numpy(), z["dq"], rtol=0, atol=gtol * scale)
+    np.testing.assert_allclose(k.grad.cpu().numpy(), z["dk"], rtol=0, atol=gtol * scale)
+
+
+def _proto_inputs(z):
+    """the selection of contrastive_loss.py:101-112,122-123 with make_golden.py's fixed sampler"""
+    index, r = z["index"], int(z["num_neg_proto"])
+    protos, temps = [], []
+    for s in range(int(z["num_sets"])):
+        e2c, cen, den = z[f"emb2cluster{s}"], z[f"centroids{s}"], z[f"density{s}"]
+        pos_id = e2c[index]
+        neg = sorted(set(range(int(e2c.max()))) - set(pos_id.tolist()))[:r]
+        ids = np.concatenate([pos_id, np.array(neg, dtype=np.int64)])
+        protos.append(torch.from_numpy(cen[ids]).to(DEV))
+        temps.append(torch.from_numpy(den[ids]).to(DEV))
+    return protos, temps
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "proto_*.npz"))))
+def test_proto_nce_matches_reference_golden(path, precision):
+    """NCELoss._compute_proto_loss (contrastive_loss.py:112-134) vs the reference's own outputs."""
+    z = np.load(path)
+    protos, temps = _proto_inputs(z)
+    if precision == "bf16" and any(p.shape[0] % 8 for p in protos):
+        pytest.skip("bf16 path needs a prototype count that is a multiple of 8")
+    q = torch.from_numpy(z["q"]).to(DEV).requires_grad_(True)
+    loss = drs_b200.proto_nce_loss(q, protos, temps, precision)
+    (loss * 2.0).backward()
+    tol, gtol = (1e-5, 1e-4) if precision == "fp32" else (2e-2, 3e-2)
+    assert abs(loss.item() - float(z["loss"])) <= tol * abs(float(z["loss"])) + 1e-5
+    scale = np.abs(z["dq"]).max() * 2.0
+    np.testing.assert_allclose(q.grad.cpu().numpy(), 2.0 * z["dq"], rtol=0, atol=gtol * scale)
+
+
+def test_nceloss_with_cluster_result_adds_proto_loss():
+    """NCELoss.forward with cluster_result (contrastive_loss.py:137-141): info loss + proto loss on
+    the module's own prototype selection, checked against the oracle on that same selection."""
+    g = torch.Generator().manual_seed(5)
+    n, dim, ncl, r = 64, 128, [96, 160], 24
+    q = torch.nn.functional.normalize(torch.randn(n, dim, generator=g), dim=1)
+    k = torch.nn.functional.normalize(torch.randn(n, dim, generator=g) * 0.5 + q, dim=1)
+    index = torch.randperm(4 * n, generator=g)[:n]
+    cr = {"emb2cluster": [], "centroids": [], "density": []}
+    for c in ncl:
+        e2c = torch.randint(0, c, (4 * n,), generator=g)
+        e2c[0] = c - 1
+        cr["emb2cluster"].append(e2c)
+        cr["centroids"].append(torch.nn.functional.normalize(torch.randn(c, dim, generator=g), dim=1).to(DEV))
+        cr["density"].append((torch.rand(c, generator=g) * 0.1 + 0.02).to(DEV))
+    cfg = {"temperature": 0.05, "precision": "fp32", "cluster": {"num_cluster": ncl, "num_neg_proto": r}}
+    crit = drs_b200.NCELoss(cfg)
+    qd = q.to(DEV).requires_grad_(True)
+    loss = crit(qd, k.to(DEV), None, cluster_result=cr, index=index)
+    loss.backward()
+    twin = drs_b200.NCELoss(cfg)                                   # same seed -> same selection
+    protos, temps = twin.select_prototypes(cr, index)
+    assert all(p.shape == (n + r, dim) for p in protos)
+    l_info, dq_info, _ = infonce.nce_info_loss(q, k, None, 0.05, dtype=torch.float64)
+    l_proto, dq_proto = infonce.proto_loss(q, [p.cpu() for p in protos], [t.cpu() for t in temps], dtype=torch.float64)
+    ref = (l_info + l_proto).item()
+    assert abs(loss.item() - ref) <= 1e-5 * abs(ref)
+    rdq = dq_info + dq_proto
+    assert (qd.grad.cpu().double() - rdq).abs().max().item() <= 1e-4 * rdq.abs().max().item()
