@@ -26,7 +26,7 @@ extern "C" {
 
 enum { DRS_OK = 0, DRS_ERR_INVALID = 1, DRS_ERR_CUDA = 2, DRS_ERR_UNSUPPORTED = 3, DRS_ERR_WORKSPACE = 4 };
 enum { DRS_F32 = 0, DRS_BF16 = 1 };
-#define DRS_MAX_K 32
+#define DRS_MAX_K 256  /* k > 32 is served in ceil(k/32) passes over the corpus */
 
 int drs_version(void);
 const char* drs_last_error(void);
@@ -53,6 +53,8 @@ int drs_get_option(const char* name, int* value);
  *   out_scores device [nq, k] fp32, descending;  out_ids device [nq, k] int64 = row + id_base
  *   ties are broken by the lower row index; when nc < k the tail is (-inf, -1).
  * DRS_BF16 needs dim % 8 == 0 and 16-byte aligned base pointers (TMA); k <= DRS_MAX_K.
+ * The running top-k lists hold 32 entries per row in registers; k > 32 runs ceil(k/32) passes, each
+ * selecting the best 32 strictly below the previous pass's last pick -- still exact.
  */
 int drs_search_workspace_bytes(int64_t nq, int64_t nc, int dim, int k, int dtype, size_t* bytes);
 int drs_search(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,

@@ -11,7 +11,7 @@ import threading
 from . import build as _build
 
 DRS_F32, DRS_BF16 = 0, 1
-DRS_MAX_K = 32
+DRS_MAX_K = 256
 
 _lock = threading.Lock()
 _lib = None

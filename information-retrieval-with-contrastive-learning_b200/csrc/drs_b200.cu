@@ -144,6 +144,7 @@ drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int 
 }
 
 constexpr int kTcColGroups = drs::GemmCfg<1>::EPI_GROUPS;
+inline size_t align256s(size_t x) { return (x + 255) & ~size_t(255); }
 constexpr size_t kWsHeaderBytes = 256;  // round-barrier counter, zeroed before every scan
 inline int num_slots(const drs::GemmShape& s) { return s.num_splits * s.col_groups; }
 
@@ -152,8 +153,10 @@ struct SearchPlan {
   int cg;          // bf16: CTA group
   int kcap;        // 16 or 32
   int k;
+  int passes;
   int grid;        // CTAs
   drs::GemmShape shape;
+  size_t bound_bytes;
   size_t ws_bytes;
 };
 
@@ -166,6 +169,7 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
   p->dtype = dtype;
   p->k = k;
   p->kcap = k <= 16 ? 16 : 32;
+  p->passes = (k + 31) / 32;   // k > 32: passes of 32, each continuing below the previous pass's last pick
   if (dtype == DRS_BF16) {
     if (di.cc_major != 10) return fail(DRS_ERR_UNSUPPORTED, "the bf16 path needs an sm_100 device (tcgen05/TMEM); this is sm_%d%d", di.cc_major, di.cc_minor);
     if (dim % 8 != 0) return fail(DRS_ERR_INVALID, "bf16 path: dim must be a multiple of 8 (TMA 16-byte row pitch), got %d", dim);
@@ -184,7 +188,8 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
   } else {
     return fail(DRS_ERR_INVALID, "unknown dtype %d", dtype);
   }
-  p->ws_bytes = kWsHeaderBytes + static_cast<size_t>(nq) * num_slots(p->shape) * p->kcap * sizeof(uint64_t);
+  p->bound_bytes = p->passes > 1 ? align256s(static_cast<size_t>(nq) * sizeof(uint64_t)) : 0;
+  p->ws_bytes = kWsHeaderBytes + p->bound_bytes + static_cast<size_t>(nq) * num_slots(p->shape) * p->kcap * sizeof(uint64_t);
   return DRS_OK;
 }
 
@@ -231,35 +236,35 @@ int launch_gemm_simt(const float* a, long long lda, const float* b, long long ld
 }
 
 template <int CG, int KCAP>
-int launch_search_tc(const SearchPlan& p, const void* queries, const void* corpus, int dim, uint64_t* ws,
-                     cudaStream_t st) {
+int launch_search_tc(const SearchPlan& p, const void* queries, const void* corpus, int dim, uint64_t* ws, int k_pass,
+                     const uint64_t* bound, cudaStream_t st) {
   using Epi = drs::TopKEpilogue<KCAP>;
-  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), p.k};
+  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound};
   return launch_gemm_tc<CG, Epi>(queries, corpus, dim, p.shape, p.grid, ep, st);
 }
 
 template <int KCAP>
-int launch_search_f32(const SearchPlan& p, const void* queries, const void* corpus, int dim, uint64_t* ws,
-                      cudaStream_t st) {
+int launch_search_f32(const SearchPlan& p, const void* queries, const void* corpus, int dim, uint64_t* ws, int k_pass,
+                      const uint64_t* bound, cudaStream_t st) {
   using Epi = drs::TopKEpilogue<KCAP>;
-  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), p.k};
+  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound};
   return launch_gemm_simt<Epi, false>(static_cast<const float*>(queries), dim, static_cast<const float*>(corpus), dim,
                                       dim, p.shape, p.grid, ep, st);
 }
 
 int launch_merge_keys(const uint64_t* ws, int64_t nq, int ncand, int k, int64_t id_base, float* out_scores,
-                      int64_t* out_ids, cudaStream_t st) {
+                      int64_t* out_ids, int ld_out, uint64_t* bound_out, cudaStream_t st) {
   const int warps_per_block = 4;
   const int blocks = static_cast<int>((nq + warps_per_block - 1) / warps_per_block);
   long long* ids = reinterpret_cast<long long*>(out_ids);
   if (ncand <= 32 * 8)
-    drs::merge_keys_kernel<8><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids);
+    drs::merge_keys_kernel<8><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids, ld_out, bound_out);
   else if (ncand <= 32 * 24)
-    drs::merge_keys_kernel<24><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids);
+    drs::merge_keys_kernel<24><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids, ld_out, bound_out);
   else if (ncand <= 32 * 40)
-    drs::merge_keys_kernel<40><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids);
+    drs::merge_keys_kernel<40><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids, ld_out, bound_out);
   else
-    drs::merge_keys_kernel<0><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids);
+    drs::merge_keys_kernel<0><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids, ld_out, bound_out);
   DRS_CUDA(cudaGetLastError());
   return DRS_OK;
 }
@@ -313,31 +318,45 @@ int drs_search_workspace_bytes(int64_t nq, int64_t nc, int dim, int k, int dtype
   return DRS_OK;
 }
 
-int drs_search_scan(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,
-                    void* workspace, size_t workspace_bytes, void* stream) {
-  if (!queries || !corpus) return fail(DRS_ERR_INVALID, "null pointer argument");
-  SearchPlan p;
-  if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
-  if (!workspace || workspace_bytes < p.ws_bytes)
-    return fail(DRS_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", p.ws_bytes, workspace_bytes);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  uint64_t* ws = reinterpret_cast<uint64_t*>(static_cast<char*>(workspace) + kWsHeaderBytes);
-  if (dtype == DRS_BF16) {
-    if ((reinterpret_cast<uintptr_t>(queries) & 15) || (reinterpret_cast<uintptr_t>(corpus) & 15))
-      return fail(DRS_ERR_INVALID, "bf16 path: queries and corpus must be 16-byte aligned");
+namespace {
+// one pass: candidates for the k_pass best keys below bound[row] (bound == nullptr: no bound)
+int scan_pass(SearchPlan& p, const void* queries, const void* corpus, int dim, void* workspace, int k_pass,
+              const uint64_t* bound, cudaStream_t st) {
+  uint64_t* ws = reinterpret_cast<uint64_t*>(static_cast<char*>(workspace) + kWsHeaderBytes + p.bound_bytes);
+  if (p.dtype == DRS_BF16) {
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
+    p.shape.round_counter = nullptr;
     if (g_opt.round_barrier && p.grid <= di.num_sms) {   // all CTAs co-resident: the barrier cannot deadlock
       DRS_CUDA(cudaMemsetAsync(workspace, 0, kWsHeaderBytes, st));
       p.shape.round_counter = static_cast<unsigned int*>(workspace);
     }
-    if (p.cg == 1) return p.kcap == 16 ? launch_search_tc<1, 16>(p, queries, corpus, dim, ws, st)
-                                       : launch_search_tc<1, 32>(p, queries, corpus, dim, ws, st);
-    return p.kcap == 16 ? launch_search_tc<2, 16>(p, queries, corpus, dim, ws, st)
-                        : launch_search_tc<2, 32>(p, queries, corpus, dim, ws, st);
+    if (p.cg == 1) return p.kcap == 16 ? launch_search_tc<1, 16>(p, queries, corpus, dim, ws, k_pass, bound, st)
+                                       : launch_search_tc<1, 32>(p, queries, corpus, dim, ws, k_pass, bound, st);
+    return p.kcap == 16 ? launch_search_tc<2, 16>(p, queries, corpus, dim, ws, k_pass, bound, st)
+                        : launch_search_tc<2, 32>(p, queries, corpus, dim, ws, k_pass, bound, st);
   }
-  return p.kcap == 16 ? launch_search_f32<16>(p, queries, corpus, dim, ws, st)
-                      : launch_search_f32<32>(p, queries, corpus, dim, ws, st);
+  return p.kcap == 16 ? launch_search_f32<16>(p, queries, corpus, dim, ws, k_pass, bound, st)
+                      : launch_search_f32<32>(p, queries, corpus, dim, ws, k_pass, bound, st);
+}
+int check_search_args(const SearchPlan& p, const void* queries, const void* corpus, void* workspace,
+                      size_t workspace_bytes) {
+  if (!queries || !corpus) return fail(DRS_ERR_INVALID, "null pointer argument");
+  if (!workspace || workspace_bytes < p.ws_bytes)
+    return fail(DRS_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", p.ws_bytes, workspace_bytes);
+  if (p.dtype == DRS_BF16 && ((reinterpret_cast<uintptr_t>(queries) & 15) || (reinterpret_cast<uintptr_t>(corpus) & 15)))
+    return fail(DRS_ERR_INVALID, "bf16 path: queries and corpus must be 16-byte aligned");
+  return DRS_OK;
+}
+}  // namespace
+
+int drs_search_scan(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  SearchPlan p;
+  if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
+  if (p.passes > 1) return fail(DRS_ERR_UNSUPPORTED, "drs_search_scan/select serve k <= 32; use drs_search for k = %d", k);
+  if (int rc = check_search_args(p, queries, corpus, workspace, workspace_bytes)) return rc;
+  return scan_pass(p, queries, corpus, dim, workspace, k, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int drs_search_select(const void* workspace, int64_t nq, int64_t nc, int dim, int dtype, int k, int64_t id_base,
@@ -345,17 +364,30 @@ int drs_search_select(const void* workspace, int64_t nq, int64_t nc, int dim, in
   if (!workspace || !out_scores || !out_ids) return fail(DRS_ERR_INVALID, "null pointer argument");
   SearchPlan p;
   if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
+  if (p.passes > 1) return fail(DRS_ERR_UNSUPPORTED, "drs_search_scan/select serve k <= 32; use drs_search for k = %d", k);
   return launch_merge_keys(reinterpret_cast<const uint64_t*>(static_cast<const char*>(workspace) + kWsHeaderBytes), nq,
-                           num_slots(p.shape) * p.kcap, k, id_base,
-                           out_scores, out_ids, static_cast<cudaStream_t>(stream));
+                           num_slots(p.shape) * p.kcap, k, id_base, out_scores, out_ids, k, nullptr,
+                           static_cast<cudaStream_t>(stream));
 }
 
 int drs_search(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,
                int64_t id_base, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
                void* stream) {
   if (!out_scores || !out_ids) return fail(DRS_ERR_INVALID, "null pointer argument");
-  if (int rc = drs_search_scan(queries, nq, corpus, nc, dim, dtype, k, workspace, workspace_bytes, stream)) return rc;
-  return drs_search_select(workspace, nq, nc, dim, dtype, k, id_base, out_scores, out_ids, stream);
+  SearchPlan p;
+  if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
+  if (int rc = check_search_args(p, queries, corpus, workspace, workspace_bytes)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(workspace);
+  uint64_t* bound = p.passes > 1 ? reinterpret_cast<uint64_t*>(base + kWsHeaderBytes) : nullptr;
+  const uint64_t* cand = reinterpret_cast<const uint64_t*>(base + kWsHeaderBytes + p.bound_bytes);
+  for (int pass = 0; pass < p.passes; ++pass) {
+    const int k_pass = std::min(32, k - 32 * pass);
+    if (int rc = scan_pass(p, queries, corpus, dim, workspace, p.passes > 1 ? k_pass : k, pass ? bound : nullptr, st)) return rc;
+    if (int rc = launch_merge_keys(cand, nq, num_slots(p.shape) * p.kcap, p.passes > 1 ? k_pass : k, id_base,
+                                   out_scores + 32 * pass, out_ids + 32 * pass, k, bound, st)) return rc;
+  }
+  return DRS_OK;
 }
 
 int drs_merge_shards(const float* scores, const int64_t* ids, int num_shards, int64_t nq, int k, float* out_scores,

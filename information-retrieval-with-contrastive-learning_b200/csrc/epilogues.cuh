@@ -20,10 +20,16 @@ struct TopKEpilogue {
     int rows_b;
     int num_slots;
     int k;
+    const uint64_t* bound;  // optional [rows_a]: only candidates with key < bound[row] are eligible
+                            // (k > KCAP is served in passes: each pass continues below the last pick)
   };
   TopKList<KCAP> list;
+  uint64_t bnd;
 
-  __device__ __forceinline__ void begin_unit(const Params&, int, int, int) { list.reset(); }
+  __device__ __forceinline__ void begin_unit(const Params& p, int row, int, int) {
+    list.reset();
+    bnd = (p.bound != nullptr && row < p.rows_a) ? p.bound[row] : ~0ull;
+  }
 
   __device__ __forceinline__ void chunk(const Params& p, int /*row*/, int col0, const uint32_t (&v)[32]) {
     const int valid = p.rows_b - col0;  // columns >= rows_b are TMA zero fill, not corpus rows
@@ -57,7 +63,7 @@ struct TopKEpilogue {
       const int j = __ffs(todo) - 1;
       todo &= todo - 1u;
       const float s = __uint_as_float(pick32(v, j));
-      const bool hit = ((mine >> j) & 1u) && (s > list.thr);
+      const bool hit = ((mine >> j) & 1u) && (s > list.thr) && (make_key(s, static_cast<uint32_t>(col0 + j)) < bnd);
       list.insert(hit ? s : -INFINITY, static_cast<uint32_t>(col0 + j), p.k);
     }
   }

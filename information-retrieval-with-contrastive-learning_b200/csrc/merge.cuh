@@ -16,13 +16,14 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
   return v;
 }
 
-// ws: [nq][ncand] packed keys (0 = empty).  out_scores [nq][k] fp32, out_ids [nq][k] int64
+// ws: [nq][ncand] packed keys (0 = empty).  out_scores / out_ids: row pitch ld_out, k columns written
 // (local row + id_base; -1 and -inf pad when fewer than k candidates exist).
 // LCAP: candidates cached per lane in registers (ncand <= 32 * LCAP), else re-read from L2.
 template <int LCAP>
 __global__ void __launch_bounds__(128)
 merge_keys_kernel(const uint64_t* __restrict__ ws, int nq, int ncand, int k, long long id_base,
-                  float* __restrict__ out_scores, long long* __restrict__ out_ids) {
+                  float* __restrict__ out_scores, long long* __restrict__ out_ids, int ld_out,
+                  uint64_t* __restrict__ bound_out) {
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (q >= nq) return;
@@ -52,11 +53,13 @@ merge_keys_kernel(const uint64_t* __restrict__ ws, int nq, int ncand, int k, lon
     }
     best = warp_max_u64(best);
     if (lane == 0) {
-      out_scores[static_cast<size_t>(q) * k + r] = best ? key_score(best) : -INFINITY;
-      out_ids[static_cast<size_t>(q) * k + r] = best ? static_cast<long long>(key_index(best)) + id_base : -1ll;
+      out_scores[static_cast<size_t>(q) * ld_out + r] = best ? key_score(best) : -INFINITY;
+      out_ids[static_cast<size_t>(q) * ld_out + r] = best ? static_cast<long long>(key_index(best)) + id_base : -1ll;
     }
     prev = best;  // best == 0 -> nothing is < 0: the remaining picks are all empty
   }
+  // the next pass (k > list capacity) continues strictly below this pass's last pick
+  if (bound_out != nullptr && lane == 0) bound_out[q] = prev;
 }
 
 // (score, id) pair order: a is better than b

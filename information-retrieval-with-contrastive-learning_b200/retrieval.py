@@ -88,7 +88,7 @@ def search(queries: torch.Tensor, corpus: torch.Tensor, k: int, *, id_base: int 
         scores = torch.empty(nq, kk, dtype=torch.float32, device=dev)
         ids = torch.empty(nq, kk, dtype=torch.int64, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        if profile is None:
+        if profile is None or kk > 32:      # the scan/select split serves single-pass searches (k <= 32)
             _lib.check(lib.drs_search(queries.data_ptr(), nq, corpus.data_ptr(), nc, dim, dt, kk, int(id_base),
                                       scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(), stream))
         else:

@@ -72,6 +72,24 @@ def test_fp32_exact_parity(nq, nc, dim, k):
     _check(q, c, k, s, i, score_rtol=1e-5, gap=2e-6)
 
 
+@pytest.mark.parametrize("dtype,nq,nc,dim,k", [(torch.bfloat16, 300, 50000, 768, 100), (torch.bfloat16, 65, 9000, 128, 33),
+                                               (torch.float32, 50, 20000, 64, 100), (torch.bfloat16, 40, 700, 64, 256),
+                                               (torch.bfloat16, 16, 90, 64, 64)])
+def test_large_k_multi_pass_is_exact(dtype, nq, nc, dim, k):
+    """BASELINE config 4's top-100: k > 32 runs ceil(k/32) passes, each continuing strictly below
+    the previous pass's last pick; must equal the oracle like a single pass (incl. k > Nc)."""
+    q, c = _data(nq, nc, dim, dtype, planted=True)
+    c[nc // 2] = c[5]
+    c[nc - 1] = c[5]                                              # ties that straddle pass boundaries
+    q[0] = c[5]
+    s, i = drs_b200.search(q, c, k)
+    tol = (1e-5, 2e-6) if dtype == torch.float32 else (2e-2, 1e-4)
+    ri = _check(q, c, k, s, i, score_rtol=tol[0], gap=tol[1])
+    assert i.shape[1] == min(k, nc)
+    assert i[0, :3].cpu().tolist() == [5, nc // 2, nc - 1]
+    assert all(len(set(r)) == i.shape[1] for r in i.cpu().tolist())
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_ties_break_to_lower_index(dtype):
     """Exact duplicates of a corpus row: equal scores, ids must come out in ascending order,
@@ -163,7 +181,7 @@ def test_closest_docs_golden_through_the_engine():
 def test_unsupported_arguments_raise_runtime_error():
     q, c = _data(4, 100, 64, torch.bfloat16)
     with pytest.raises(RuntimeError, match="exceeds the engine limit"):
-        drs_b200.search(q, c, 64)
+        drs_b200.search(q[:, :64].repeat(1, 1), torch.cat([c] * 4), 300)
     with pytest.raises(RuntimeError, match="multiple of 8"):
         drs_b200.search(q[:, :60].contiguous(), c[:, :60].contiguous(), 3)
 
