@@ -70,6 +70,18 @@ int drs_search_select(const void* workspace, int64_t nq, int64_t nc, int dim, in
                       float* out_scores, int64_t* out_ids, void* stream);
 
 /*
+ * Exact squared-L2 nearest neighbours (same kernel, ranked value 2 x.c - |c|^2, reported as
+ * |x|^2 + |c|^2 - 2 x.c, ascending; ties -> lower row).
+ * Replaces: faiss GpuIndexFlatL2.search as used for the k-means assignment at
+ * src/contrastor/utils.py:64-67 (`D, I = index.search(x, 1)`).  PARITY UNPINNED: faiss is an
+ * unpinned dependency that is not part of the reference tree.
+ */
+int drs_search_l2_workspace_bytes(int64_t nq, int64_t nc, int dim, int k, int dtype, size_t* bytes);
+int drs_search_l2(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,
+                  int64_t id_base, float* out_dist, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/*
  * Merge the per-shard top-k lists of a row-sharded corpus (after the all-gather):
  *   scores device [num_shards, nq, k], ids device [num_shards, nq, k] (id < 0 = empty slot)
  *   -> out_scores / out_ids device [nq, k], ordered by (score desc, id asc).

@@ -14,9 +14,10 @@ Everything computes in hand-written sm_100a CUDA behind the C ABI of include/drs
 from . import _lib, build
 from ._lib import get_option, set_option
 from .loss import InfoNCE, NCELoss, info_nce_loss, proto_nce_loss
-from .retrieval import DenseIndex, ShardedDenseIndex, all_gather_topk, merge_shards, search, shard_bounds
+from .retrieval import (DenseIndex, FlatL2Index, ShardedDenseIndex, all_gather_topk, flat_l2_search, merge_shards, search,
+                        shard_bounds)
 
 __all__ = [
-    "search", "merge_shards", "DenseIndex", "ShardedDenseIndex", "all_gather_topk", "shard_bounds",
+    "search", "flat_l2_search", "FlatL2Index", "merge_shards", "DenseIndex", "ShardedDenseIndex", "all_gather_topk", "shard_bounds",
     "NCELoss", "InfoNCE", "info_nce_loss", "proto_nce_loss", "set_option", "get_option", "build",
 ]

@@ -237,34 +237,45 @@ int launch_gemm_simt(const float* a, long long lda, const float* b, long long ld
 
 template <int CG, int KCAP>
 int launch_search_tc(const SearchPlan& p, const void* queries, const void* corpus, int dim, uint64_t* ws, int k_pass,
-                     const uint64_t* bound, cudaStream_t st) {
+                     const uint64_t* bound, const float* col_bias, cudaStream_t st) {
+  if (col_bias != nullptr) {
+    using Epi = drs::TopKEpilogue<KCAP, true>;
+    typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, col_bias, 2.0f};
+    return launch_gemm_tc<CG, Epi>(queries, corpus, dim, p.shape, p.grid, ep, st);
+  }
   using Epi = drs::TopKEpilogue<KCAP>;
-  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound};
+  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, nullptr, 1.0f};
   return launch_gemm_tc<CG, Epi>(queries, corpus, dim, p.shape, p.grid, ep, st);
 }
 
 template <int KCAP>
 int launch_search_f32(const SearchPlan& p, const void* queries, const void* corpus, int dim, uint64_t* ws, int k_pass,
-                      const uint64_t* bound, cudaStream_t st) {
+                      const uint64_t* bound, const float* col_bias, cudaStream_t st) {
+  if (col_bias != nullptr) {
+    using Epi = drs::TopKEpilogue<KCAP, true>;
+    typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, col_bias, 2.0f};
+    return launch_gemm_simt<Epi, false>(static_cast<const float*>(queries), dim, static_cast<const float*>(corpus),
+                                        dim, dim, p.shape, p.grid, ep, st);
+  }
   using Epi = drs::TopKEpilogue<KCAP>;
-  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound};
+  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, nullptr, 1.0f};
   return launch_gemm_simt<Epi, false>(static_cast<const float*>(queries), dim, static_cast<const float*>(corpus), dim,
                                       dim, p.shape, p.grid, ep, st);
 }
 
 int launch_merge_keys(const uint64_t* ws, int64_t nq, int ncand, int k, int64_t id_base, float* out_scores,
-                      int64_t* out_ids, int ld_out, uint64_t* bound_out, cudaStream_t st) {
+                      int64_t* out_ids, int ld_out, uint64_t* bound_out, const float* row_term, cudaStream_t st) {
   const int warps_per_block = 4;
   const int blocks = static_cast<int>((nq + warps_per_block - 1) / warps_per_block);
   long long* ids = reinterpret_cast<long long*>(out_ids);
   if (ncand <= 32 * 8)
-    drs::merge_keys_kernel<8><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids, ld_out, bound_out);
+    drs::merge_keys_kernel<8><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids, ld_out, bound_out, row_term);
   else if (ncand <= 32 * 24)
-    drs::merge_keys_kernel<24><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids, ld_out, bound_out);
+    drs::merge_keys_kernel<24><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids, ld_out, bound_out, row_term);
   else if (ncand <= 32 * 40)
-    drs::merge_keys_kernel<40><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids, ld_out, bound_out);
+    drs::merge_keys_kernel<40><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids, ld_out, bound_out, row_term);
   else
-    drs::merge_keys_kernel<0><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids, ld_out, bound_out);
+    drs::merge_keys_kernel<0><<<blocks, 128, 0, st>>>(ws, (int)nq, ncand, k, id_base, out_scores, ids, ld_out, bound_out, row_term);
   DRS_CUDA(cudaGetLastError());
   return DRS_OK;
 }
@@ -321,8 +332,8 @@ int drs_search_workspace_bytes(int64_t nq, int64_t nc, int dim, int k, int dtype
 namespace {
 // one pass: candidates for the k_pass best keys below bound[row] (bound == nullptr: no bound)
 int scan_pass(SearchPlan& p, const void* queries, const void* corpus, int dim, void* workspace, int k_pass,
-              const uint64_t* bound, cudaStream_t st) {
-  uint64_t* ws = reinterpret_cast<uint64_t*>(static_cast<char*>(workspace) + kWsHeaderBytes + p.bound_bytes);
+              const uint64_t* bound, cudaStream_t st, const float* col_bias = nullptr, size_t extra_bytes = 0) {
+  uint64_t* ws = reinterpret_cast<uint64_t*>(static_cast<char*>(workspace) + kWsHeaderBytes + p.bound_bytes + extra_bytes);
   if (p.dtype == DRS_BF16) {
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
@@ -331,13 +342,13 @@ int scan_pass(SearchPlan& p, const void* queries, const void* corpus, int dim, v
       DRS_CUDA(cudaMemsetAsync(workspace, 0, kWsHeaderBytes, st));
       p.shape.round_counter = static_cast<unsigned int*>(workspace);
     }
-    if (p.cg == 1) return p.kcap == 16 ? launch_search_tc<1, 16>(p, queries, corpus, dim, ws, k_pass, bound, st)
-                                       : launch_search_tc<1, 32>(p, queries, corpus, dim, ws, k_pass, bound, st);
-    return p.kcap == 16 ? launch_search_tc<2, 16>(p, queries, corpus, dim, ws, k_pass, bound, st)
-                        : launch_search_tc<2, 32>(p, queries, corpus, dim, ws, k_pass, bound, st);
+    if (p.cg == 1) return p.kcap == 16 ? launch_search_tc<1, 16>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, st)
+                                       : launch_search_tc<1, 32>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, st);
+    return p.kcap == 16 ? launch_search_tc<2, 16>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, st)
+                        : launch_search_tc<2, 32>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, st);
   }
-  return p.kcap == 16 ? launch_search_f32<16>(p, queries, corpus, dim, ws, k_pass, bound, st)
-                      : launch_search_f32<32>(p, queries, corpus, dim, ws, k_pass, bound, st);
+  return p.kcap == 16 ? launch_search_f32<16>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, st)
+                      : launch_search_f32<32>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, st);
 }
 int check_search_args(const SearchPlan& p, const void* queries, const void* corpus, void* workspace,
                       size_t workspace_bytes) {
@@ -366,7 +377,7 @@ int drs_search_select(const void* workspace, int64_t nq, int64_t nc, int dim, in
   if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
   if (p.passes > 1) return fail(DRS_ERR_UNSUPPORTED, "drs_search_scan/select serve k <= 32; use drs_search for k = %d", k);
   return launch_merge_keys(reinterpret_cast<const uint64_t*>(static_cast<const char*>(workspace) + kWsHeaderBytes), nq,
-                           num_slots(p.shape) * p.kcap, k, id_base, out_scores, out_ids, k, nullptr,
+                           num_slots(p.shape) * p.kcap, k, id_base, out_scores, out_ids, k, nullptr, nullptr,
                            static_cast<cudaStream_t>(stream));
 }
 
@@ -385,7 +396,54 @@ int drs_search(const void* queries, int64_t nq, const void* corpus, int64_t nc, 
     const int k_pass = std::min(32, k - 32 * pass);
     if (int rc = scan_pass(p, queries, corpus, dim, workspace, p.passes > 1 ? k_pass : k, pass ? bound : nullptr, st)) return rc;
     if (int rc = launch_merge_keys(cand, nq, num_slots(p.shape) * p.kcap, p.passes > 1 ? k_pass : k, id_base,
-                                   out_scores + 32 * pass, out_ids + 32 * pass, k, bound, st)) return rc;
+                                   out_scores + 32 * pass, out_ids + 32 * pass, k, bound, nullptr, st)) return rc;
+  }
+  return DRS_OK;
+}
+
+namespace {
+size_t l2_extra_bytes(int64_t nq, int64_t nc) { return align256s(nc * sizeof(float)) + align256s(nq * sizeof(float)); }
+}
+
+int drs_search_l2_workspace_bytes(int64_t nq, int64_t nc, int dim, int k, int dtype, size_t* bytes) {
+  if (!bytes) return fail(DRS_ERR_INVALID, "bytes is null");
+  SearchPlan p;
+  if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
+  *bytes = p.ws_bytes + l2_extra_bytes(nq, nc);
+  return DRS_OK;
+}
+
+int drs_search_l2(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,
+                  int64_t id_base, float* out_dist, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  if (!out_dist || !out_ids) return fail(DRS_ERR_INVALID, "null pointer argument");
+  SearchPlan p;
+  if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
+  const size_t extra = l2_extra_bytes(nq, nc);
+  p.ws_bytes += extra;
+  if (int rc = check_search_args(p, queries, corpus, workspace, workspace_bytes)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(workspace);
+  // layout: [header | bound | -|c|^2 per corpus row | |x|^2 per query | candidates]
+  uint64_t* bound = p.passes > 1 ? reinterpret_cast<uint64_t*>(base + kWsHeaderBytes) : nullptr;
+  float* col_bias = reinterpret_cast<float*>(base + kWsHeaderBytes + p.bound_bytes);
+  float* row_term = reinterpret_cast<float*>(base + kWsHeaderBytes + p.bound_bytes + align256s(nc * sizeof(float)));
+  const uint64_t* cand = reinterpret_cast<const uint64_t*>(base + kWsHeaderBytes + p.bound_bytes + extra);
+  const int bc = static_cast<int>((nc + 7) / 8), bq = static_cast<int>((nq + 7) / 8);
+  if (dtype == DRS_BF16) {
+    drs::row_sqnorm_kernel<__nv_bfloat16><<<bc, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(corpus), nc, dim, -1.f, col_bias);
+    drs::row_sqnorm_kernel<__nv_bfloat16><<<bq, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(queries), nq, dim, 1.f, row_term);
+  } else {
+    drs::row_sqnorm_kernel<float><<<bc, 256, 0, st>>>(static_cast<const float*>(corpus), nc, dim, -1.f, col_bias);
+    drs::row_sqnorm_kernel<float><<<bq, 256, 0, st>>>(static_cast<const float*>(queries), nq, dim, 1.f, row_term);
+  }
+  DRS_CUDA(cudaGetLastError());
+  for (int pass = 0; pass < p.passes; ++pass) {
+    const int k_pass = std::min(32, k - 32 * pass);
+    if (int rc = scan_pass(p, queries, corpus, dim, workspace, p.passes > 1 ? k_pass : k, pass ? bound : nullptr, st,
+                           col_bias, extra)) return rc;
+    if (int rc = launch_merge_keys(cand, nq, num_slots(p.shape) * p.kcap, p.passes > 1 ? k_pass : k, id_base,
+                                   out_dist + 32 * pass, out_ids + 32 * pass, k, bound, row_term, st)) return rc;
   }
   return DRS_OK;
 }

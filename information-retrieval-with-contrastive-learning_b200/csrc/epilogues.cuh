@@ -12,7 +12,7 @@ namespace drs {
 // TfidfDocRanker.closest_docs (preprocessing/drqa/retriever/tfidf_doc_ranker.py:67-73) for the
 // dense scores of src/evaluation.py:110-115.  Output: KCAP packed keys per (claim, split) in the
 // workspace; merge.cuh reduces the splits to the final k.
-template <int KCAP>
+template <int KCAP, bool BIASED = false>
 struct TopKEpilogue {
   struct Params {
     uint64_t* ws;  // [rows_a][num_slots][KCAP]   slot = split * (column groups per tile) + group
@@ -22,6 +22,8 @@ struct TopKEpilogue {
     int k;
     const uint64_t* bound;  // optional [rows_a]: only candidates with key < bound[row] are eligible
                             // (k > KCAP is served in passes: each pass continues below the last pick)
+    const float* col_bias;  // BIASED: ranked value = score_scale * dot + col_bias[col]
+    float score_scale;      //   (squared-L2 search: 2 x.c - |c|^2, src/contrastor/utils.py:64-67)
   };
   TopKList<KCAP> list;
   uint64_t bnd;
@@ -31,7 +33,22 @@ struct TopKEpilogue {
     bnd = (p.bound != nullptr && row < p.rows_a) ? p.bound[row] : ~0ull;
   }
 
-  __device__ __forceinline__ void chunk(const Params& p, int /*row*/, int col0, const uint32_t (&v)[32]) {
+  __device__ __forceinline__ void chunk(const Params& p, int row, int col0, const uint32_t (&raw)[32]) {
+    if constexpr (BIASED) {
+      uint32_t t[32];
+      const int nv = p.rows_b - col0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float b = (j < nv) ? __ldg(p.col_bias + col0 + j) : 0.f;
+        t[j] = __float_as_uint(fmaf(p.score_scale, __uint_as_float(raw[j]), b));
+      }
+      scan(p, row, col0, t);
+    } else {
+      scan(p, row, col0, raw);
+    }
+  }
+
+  __device__ __forceinline__ void scan(const Params& p, int /*row*/, int col0, const uint32_t (&v)[32]) {
     const int valid = p.rows_b - col0;  // columns >= rows_b are TMA zero fill, not corpus rows
     float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
     if (valid >= 32) {

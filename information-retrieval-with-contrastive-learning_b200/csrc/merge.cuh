@@ -3,6 +3,8 @@
 // One warp per claim.  Keys/pairs are unique per claim, so "the best candidate strictly worse
 // than the previous pick" walks the order without mutating the candidate set.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "topk.cuh"
 
 namespace drs {
@@ -23,7 +25,7 @@ template <int LCAP>
 __global__ void __launch_bounds__(128)
 merge_keys_kernel(const uint64_t* __restrict__ ws, int nq, int ncand, int k, long long id_base,
                   float* __restrict__ out_scores, long long* __restrict__ out_ids, int ld_out,
-                  uint64_t* __restrict__ bound_out) {
+                  uint64_t* __restrict__ bound_out, const float* __restrict__ row_term) {
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (q >= nq) return;
@@ -53,7 +55,10 @@ merge_keys_kernel(const uint64_t* __restrict__ ws, int nq, int ncand, int k, lon
     }
     best = warp_max_u64(best);
     if (lane == 0) {
-      out_scores[static_cast<size_t>(q) * ld_out + r] = best ? key_score(best) : -INFINITY;
+      // row_term: squared-L2 search reports |x|^2 - (2 x.c - |c|^2), ascending = ranked value descending
+      float sc = best ? key_score(best) : -INFINITY;
+      if (row_term != nullptr) sc = best ? fmaxf(row_term[q] - sc, 0.f) : INFINITY;
+      out_scores[static_cast<size_t>(q) * ld_out + r] = sc;
       out_ids[static_cast<size_t>(q) * ld_out + r] = best ? static_cast<long long>(key_index(best)) + id_base : -1ll;
     }
     prev = best;  // best == 0 -> nothing is < 0: the remaining picks are all empty
@@ -109,6 +114,21 @@ merge_pairs_kernel(const float* __restrict__ in_scores, const long long* __restr
     ps = bs;
     pi = bi;
   }
+}
+
+// |row|^2 in fp32 for fp32 or bf16 rows; out[r] = sign * |row|^2.  One warp per row.
+template <typename T>
+__global__ void row_sqnorm_kernel(const T* __restrict__ x, long long rows, int dim, float sign, float* __restrict__ out) {
+  const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float acc = 0.f;
+  for (int d = threadIdx.x & 31; d < dim; d += 32) {
+    const float v = static_cast<float>(x[row * dim + d]);
+    acc = fmaf(v, v, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) out[row] = sign * acc;
 }
 
 }  // namespace drs

@@ -103,6 +103,83 @@ def search(queries: torch.Tensor, corpus: torch.Tensor, k: int, *, id_base: int 
     return scores, ids
 
 
+def flat_l2_search(x: torch.Tensor, centroids: torch.Tensor, k: int = 1, *, id_base: int = 0):
+    """Exact squared-L2 nearest neighbours: what ``faiss.GpuIndexFlatL2.search(x, k)`` returns at
+    src/contrastor/utils.py:64-67 (the k-means assignment of ``run_kmeans``).
+
+    x [n, D], centroids [Nc, D]: CUDA, same dtype (fp32 -> exact FFMA path like faiss's
+    ``useFloat16 = False`` at utils.py:44; bf16 -> tcgen05 path).  Returns (D fp32 [n, k'] ascending
+    squared distances, I int64 [n, k']), k' = min(k, Nc), ties -> lower index.
+    PARITY UNPINNED against faiss itself (unpinned, not vendored, not installed)."""
+    _check_matrix("x", x)
+    _check_matrix("centroids", centroids)
+    if x.device != centroids.device:
+        raise RuntimeError("x and centroids must be on the same device")
+    if x.shape[1] != centroids.shape[1]:
+        raise ValueError(f"dimension mismatch: x {tuple(x.shape)} vs centroids {tuple(centroids.shape)}")
+    if x.dtype != centroids.dtype:
+        x = x.to(centroids.dtype)
+    if k <= 0:
+        raise ValueError(f"k must be positive, got {k}")
+    n, dim = x.shape
+    nc = centroids.shape[0]
+    kk = min(int(k), nc)
+    dev = x.device
+    if n == 0 or nc == 0:
+        return (torch.empty(n, kk, dtype=torch.float32, device=dev), torch.empty(n, kk, dtype=torch.int64, device=dev))
+    if kk > _lib.DRS_MAX_K:
+        raise RuntimeError(f"k={kk} exceeds the engine limit of {_lib.DRS_MAX_K}")
+    x = x.contiguous()
+    centroids = centroids.contiguous()
+    lib = _lib.load()
+    dt = _DTYPES[centroids.dtype]
+    with torch.cuda.device(dev):
+        need = ctypes.c_size_t(0)
+        _lib.check(lib.drs_search_l2_workspace_bytes(n, nc, dim, kk, dt, ctypes.byref(need)))
+        ws = _workspace(dev, need.value)
+        dist = torch.empty(n, kk, dtype=torch.float32, device=dev)
+        ids = torch.empty(n, kk, dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.drs_search_l2(x.data_ptr(), n, centroids.data_ptr(), nc, dim, dt, kk, int(id_base),
+                                     dist.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    return dist, ids
+
+
+class FlatL2Index:
+    """The slice of ``faiss.GpuIndexFlatL2`` that ``run_kmeans`` uses (src/contrastor/utils.py:39-47,
+    :64-67): ``add`` vectors, ``search(x, k) -> (D, I)`` as numpy arrays, ``ntotal``, ``reset``."""
+
+    def __init__(self, d: int, device=None, dtype: torch.dtype = torch.float32):
+        self.d = int(d)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.dtype = dtype                      # fp32 == faiss cfg.useFloat16 = False (utils.py:44)
+        self._chunks = []
+        self._mat = None
+
+    @property
+    def ntotal(self) -> int:
+        return sum(c.shape[0] for c in self._chunks)
+
+    def reset(self):
+        self._chunks, self._mat = [], None
+
+    def add(self, x):
+        x = torch.as_tensor(x)
+        if x.dim() != 2 or x.shape[1] != self.d:
+            raise ValueError(f"add expects [n, {self.d}] vectors")
+        self._chunks.append(x.to(device=self.device, dtype=self.dtype).contiguous())
+        self._mat = None
+
+    def search(self, x, k: int = 1):
+        if not self._chunks:
+            raise RuntimeError("search on an empty index")
+        if self._mat is None:
+            self._mat = self._chunks[0] if len(self._chunks) == 1 else torch.cat(self._chunks)
+            self._chunks = [self._mat]
+        d, i = flat_l2_search(torch.as_tensor(x).to(device=self.device, dtype=self.dtype), self._mat, k)
+        return d.cpu().numpy(), i.cpu().numpy()
+
+
 def merge_shards(scores: torch.Tensor, ids: torch.Tensor):
     """[g, nq, k] per-shard lists (id < 0 = empty) -> [nq, k] by (score desc, id asc)."""
     if scores.dim() != 3 or scores.shape != ids.shape:

@@ -230,3 +230,33 @@ def test_full_size_properties_config2():
         ii.append(b)
     ms, mi = drs_b200.merge_shards(torch.stack(ss), torch.stack(ii))
     assert torch.equal(mi, i) and torch.equal(ms, s)
+
+
+@pytest.mark.parametrize("dtype,n,nc,dim,k", [(torch.float32, 2000, 4096, 128, 1), (torch.float32, 300, 8192, 128, 5),
+                                              (torch.float32, 77, 333, 50, 40), (torch.bfloat16, 1000, 6144, 128, 1)])
+def test_flat_l2_search_kmeans_assignment(dtype, n, nc, dim, k):
+    """src/contrastor/utils.py:64-67: `D, I = index.search(x, 1)` against 4096/6144/8192 centroids
+    (config.yaml num_cluster).  Oracle = exact squared-L2 argmin in fp64 (PARITY UNPINNED vs faiss)."""
+    g = torch.Generator(device=DEV).manual_seed(1337)
+    cen = torch.randn(nc, dim, generator=g, device=DEV)
+    lab = torch.randint(0, nc, (n,), generator=g, device=DEV)
+    x = cen[lab] + 0.3 * torch.randn(n, dim, generator=g, device=DEV)
+    cen, x = cen.to(dtype), x.to(dtype)
+    d, i = drs_b200.flat_l2_search(x, cen, k)
+    rd, ri = dense_topk.flat_l2_search(x.cpu(), cen.cpu(), k)
+    assert torch.equal(i[:, 0].cpu(), lab.cpu()) and torch.equal(ri[:, 0], lab.cpu())
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    torch.testing.assert_close(d.cpu(), rd, rtol=tol, atol=tol * float(rd.max()))
+    assert torch.all(d[:, 1:] >= d[:, :-1])
+    gap = (rd[:, 1:] - rd[:, :-1]) if k > 1 else None
+    if gap is not None and dtype == torch.float32:
+        strict = torch.ones_like(ri, dtype=torch.bool)
+        strict[:, 1:] &= gap > 1e-3
+        strict[:, :-1] &= gap > 1e-3
+        assert torch.equal(i.cpu()[strict], ri[strict])
+    index = drs_b200.FlatL2Index(dim, dtype=dtype)
+    index.add(cen[: nc // 2].cpu().float().numpy())
+    index.add(cen[nc // 2:].cpu().float().numpy())
+    assert index.ntotal == nc
+    dd, ii = index.search(x[:50].cpu().float().numpy(), 1)
+    assert ii.shape == (50, 1) and ii.dtype == np.int64 and [int(v) for v in ii[:, 0]] == lab[:50].cpu().tolist()
