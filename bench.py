@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--workload", default="fever_sentences_25M", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (N=1 only runs it)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for the baseline sample")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the small-batch (HBM-bound) sweep and the InfoNCE config line")
     return ap.parse_args()
 
 
@@ -162,6 +164,40 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bench_infonce(torch, drs_b200, dev, peaks, n=4096, dim=768, temperature=0.05, reps=20):
+    """BASELINE configs[3] (contrastor training step): NCELoss forward + backward on one GPU through the
+    module a trainer calls (contrastive_module.py:86-87 -> train.py:147), CUDA events, inputs resident."""
+    g = torch.Generator(device=dev).manual_seed(1337)
+    q = torch.nn.functional.normalize(torch.randn(n, dim, generator=g, device=dev), dim=1).requires_grad_(True)
+    kk = torch.nn.functional.normalize(torch.randn(n, dim, generator=g, device=dev) * 0.5 + q.detach(), dim=1)
+    kk.requires_grad_(True)
+    crit = drs_b200.NCELoss({"temperature": temperature})
+
+    def step():
+        q.grad = None
+        kk.grad = None
+        loss = crit(q, kk, None)
+        loss.backward()
+        return loss
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    # algorithmic flops: S = F F^T forward (2 (2N)^2 D), backward recompute + dF = H F (2 x 2 (2N)^2 D)
+    flops = 3 * 2.0 * (2 * n) ** 2 * dim
+    return {"workload": f"NCELoss fwd+bwd, batch {n} x {dim} (2N = {2 * n} rows), T = {temperature}, bf16 MMA / fp32 softmax",
+            "ms_per_step": ms, "steps_per_s": 1e3 / ms, "tflops": flops / (ms * 1e-3) / 1e12,
+            "mma_frac": flops / (ms * 1e-3) / 1e12 / peaks["tflops"],
+            "logit_matrix_bytes_never_materialised": 4 * (2 * n) ** 2}
+
+
 # --------------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import torch
@@ -246,6 +282,39 @@ def run_b200(args):
            "h2d_bytes_per_step": queries_host.numel() * queries_host.element_size(),
            "d2h_bytes_per_step": out_s.numel() * 4 + out_i.numel() * 8}
 
+    # ---- the small-query-batch, bandwidth-bound regime: B claims share one
+    #      corpus pass, intensity = B flop/byte, HBM-bound below the ridge (~212).  Same corpus, same call.
+    regimes = []
+    if not args.no_extras:
+        for bq in (1, 16, 64, 128, 256):
+            qs = queries[:bq].contiguous()
+            rprof = []
+            for _ in range(3):
+                index.search(qs, k)
+            reps = 10
+            ms = timed_loop(lambda: index.search(qs, k, profile=rprof), reps) / reps
+            kms = sum(a.elapsed_time(b) for a, b in rprof) / max(1, len(rprof))
+            if world > 1:
+                t = torch.tensor([kms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                kms = t.item()
+            rows_r = hi - lo
+            byt = rows_r * dim * 2 + bq * dim * 2 + bq * k * 12
+            flp = 2.0 * bq * rows_r * dim
+            gbs = byt / (kms * 1e-3) / 1e9
+            tfl = flp / (kms * 1e-3) / 1e12
+            t_hbm, t_mma = byt / (peaks["hbm_gbs"] * 1e9), flp / (peaks["tflops"] * 1e12)
+            regimes.append({"claims_per_pass": bq, "ms_per_step": ms, "scan_kernel_ms": kms,
+                            "claims_per_s": bq / (ms * 1e-3), "hbm_gbs_per_gpu": gbs,
+                            "hbm_frac": gbs / peaks["hbm_gbs"], "mma_frac": tfl / peaks["tflops"],
+                            "bound": "hbm" if t_hbm >= t_mma else "tensor",
+                            "roofline_frac": max(t_hbm, t_mma) / (kms * 1e-3)})
+
+    # ---- BASELINE configs[3]: in-batch InfoNCE, batch 4096 x 768, fused logits + softmax-CE fwd/bwd
+    infonce_line = None
+    if not args.no_extras and rank == 0:
+        infonce_line = bench_infonce(torch, drs_b200, dev, peaks)
+
     # ---- roofline of the dominant kernel (the fused score GEMM + top-k scan), per launch = per rank shard
     rows = hi - lo
     flops = 2.0 * nq * rows * dim
@@ -275,6 +344,10 @@ def run_b200(args):
                        "l2": "corpus shard (>= 4.8 GB) exceeds the 126 MB L2 every step; no flush needed"},
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clk.summary(), "roofline": roofline,
         }
+        if regimes:
+            line["small_batch_regime"] = regimes
+        if infonce_line:
+            line["infonce_config"] = infonce_line
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_reference_rate(nq, nc, dim, k, args.cpu_seconds)
         print(json.dumps(line), flush=True)

@@ -26,7 +26,7 @@ extern "C" {
 
 enum { DRS_OK = 0, DRS_ERR_INVALID = 1, DRS_ERR_CUDA = 2, DRS_ERR_UNSUPPORTED = 3, DRS_ERR_WORKSPACE = 4 };
 enum { DRS_F32 = 0, DRS_BF16 = 1 };
-#define DRS_MAX_K 256  /* k > 32 is served in ceil(k/32) passes over the corpus */
+#define DRS_MAX_K 256  /* k > 32: adaptive passes over the corpus (at most ceil(k/32), usually one) */
 
 int drs_version(void);
 const char* drs_last_error(void);
@@ -53,13 +53,20 @@ int drs_get_option(const char* name, int* value);
  *   out_scores device [nq, k] fp32, descending;  out_ids device [nq, k] int64 = row + id_base
  *   ties are broken by the lower row index; when nc < k the tail is (-inf, -1).
  * DRS_BF16 needs dim % 8 == 0 and 16-byte aligned base pointers (TMA); k <= DRS_MAX_K.
- * The running top-k lists hold 32 entries per row in registers; k > 32 runs ceil(k/32) passes, each
- * selecting the best 32 strictly below the previous pass's last pick -- still exact.
+ * The running top-k lists hold 32 entries per (claim, corpus split) in registers.  k > 32 stays exact:
+ * the select emits picks only while no split's full list could hide a better row, and a claim that stops
+ * early is continued by a rescan strictly below its last pick.  At most ceil(k/32) passes are enqueued;
+ * a pass with no open claim returns at once on the device (one pass does all the work unless more than
+ * 32 of a claim's top-k fall into one of the ~74+ splits).
  */
 int drs_search_workspace_bytes(int64_t nq, int64_t nc, int dim, int k, int dtype, size_t* bytes);
 int drs_search(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,
                int64_t id_base, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
                void* stream);
+
+/* Debug: after a k > 32 drs_search / drs_search_l2 on `workspace`, out[p] = the number of claims that
+ * pass p left open (needing a rescan below their last certain pick).  Synchronises the stream. */
+int drs_debug_open_claims(const void* workspace, unsigned int out[8], void* stream);
 
 /* The two phases of drs_search, separately launchable (drs_search == scan then select on the same
  * stream): `scan` is the fused score GEMM + per-row running top-k that leaves the per-split
@@ -80,6 +87,25 @@ int drs_search_l2_workspace_bytes(int64_t nq, int64_t nc, int dim, int k, int dt
 int drs_search_l2(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,
                   int64_t id_base, float* out_dist, int64_t* out_ids, void* workspace, size_t workspace_bytes,
                   void* stream);
+
+/*
+ * Candidate-restricted re-rank: score each claim against ITS OWN candidate rows only and keep the best k.
+ * Replaces: the dense stage of the report's pipeline "TF-IDF top-100 -> contrastive re-rank -> top-15"
+ * (report.pdf section 3.2) at the call site src/evaluation.py:105-116, fed by the sparse candidates of
+ * documents_filtering (src/evaluation.py:57-83) / closest_docs (tfidf_doc_ranker.py:60-75).
+ *   cand_ids device [nq, num_cand] int64 corpus rows; id < 0 or >= nc is padding and is ignored
+ *   out_scores device [nq, k] fp32 descending; out_ids device [nq, k] int64 (the candidate's row);
+ *   ties -> lower row; a row listed twice is reported once; missing entries are (-inf, -1).
+ * HBM-bound gather (one corpus row read per pair); no workspace.  1 <= k <= num_cand.
+ */
+int drs_rerank(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype,
+               const int64_t* cand_ids, int num_cand, int k, float* out_scores, int64_t* out_ids, void* stream);
+
+/*
+ * out[i] = a[i] . b[i] for two [n, dim] matrices.
+ * Replaces: `(clm_vec * evdn_vec).sum(dim=-1)` of the commented dense evaluation, src/evaluation.py:112,115.
+ */
+int drs_pair_scores(const void* a, const void* b, int64_t n, int dim, int dtype, float* out, void* stream);
 
 /*
  * Merge the per-shard top-k lists of a row-sharded corpus (after the all-gather):

@@ -26,10 +26,13 @@ _SIGNATURES = {
     "drs_debug_hang_report": (c_int, [ctypes.POINTER(ctypes.c_uint * 6)]),
     "drs_search_workspace_bytes": (c_int, [c_i64, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_sz)]),
     "drs_search": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "drs_debug_open_claims": (c_int, [c_vp, ctypes.POINTER(ctypes.c_uint * 8), c_vp]),
     "drs_search_scan": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
     "drs_search_select": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
     "drs_search_l2_workspace_bytes": (c_int, [c_i64, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_sz)]),
     "drs_search_l2": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "drs_rerank": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
+    "drs_pair_scores": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
     "drs_merge_shards": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp]),
     "drs_infonce_workspace_bytes": (c_int, [c_i64, c_int, c_i64, c_int, ctypes.POINTER(c_sz)]),
     "drs_infonce_forward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_f32, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),

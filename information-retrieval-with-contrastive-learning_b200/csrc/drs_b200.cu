@@ -15,6 +15,7 @@
 #include "gemm_tc.cuh"
 #include "infonce.cuh"
 #include "merge.cuh"
+#include "rerank.cuh"
 
 namespace {
 
@@ -140,12 +141,14 @@ drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int 
   s.b_hint = g_opt.b_hint;
   s.stagger_cycles = g_opt.stagger_cycles;
   s.round_counter = nullptr;
+  s.active = nullptr;
   return s;
 }
 
 constexpr int kTcColGroups = drs::GemmCfg<1>::EPI_GROUPS;
 inline size_t align256s(size_t x) { return (x + 255) & ~size_t(255); }
-constexpr size_t kWsHeaderBytes = 256;  // round-barrier counter, zeroed before every scan
+constexpr size_t kWsRoundBytes = 256;   // round-barrier counter, zeroed before every scan
+constexpr size_t kWsHeaderBytes = 512;  // + per-pass "claims still open" counters of the adaptive k > 32 search
 inline int num_slots(const drs::GemmShape& s) { return s.num_splits * s.col_groups; }
 
 struct SearchPlan {
@@ -188,7 +191,8 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
   } else {
     return fail(DRS_ERR_INVALID, "unknown dtype %d", dtype);
   }
-  p->bound_bytes = p->passes > 1 ? align256s(static_cast<size_t>(nq) * sizeof(uint64_t)) : 0;
+  // k > 32: per claim a continuation bound (u64) and the count of picks already emitted (int)
+  p->bound_bytes = p->passes > 1 ? align256s(static_cast<size_t>(nq) * sizeof(uint64_t)) + align256s(static_cast<size_t>(nq) * sizeof(int)) : 0;
   p->ws_bytes = kWsHeaderBytes + p->bound_bytes + static_cast<size_t>(nq) * num_slots(p->shape) * p->kcap * sizeof(uint64_t);
   return DRS_OK;
 }
@@ -280,6 +284,30 @@ int launch_merge_keys(const uint64_t* ws, int64_t nq, int ncand, int k, int64_t 
   return DRS_OK;
 }
 
+template <int SL>
+int launch_merge_runs_sl(const uint64_t* ws, int64_t nq, int nslots, int k, int64_t id_base, float* out_scores,
+                         int64_t* out_ids, uint64_t* bound, int* done, const unsigned int* active_in,
+                         unsigned int* remaining_out, const float* row_term, cudaStream_t st) {
+  const int blocks = static_cast<int>((nq + 3) / 4);
+  drs::merge_runs_kernel<SL, 32><<<blocks, 128, 0, st>>>(ws, (int)nq, nslots, k, id_base, out_scores,
+                                                          reinterpret_cast<long long*>(out_ids), k, bound, done,
+                                                          active_in, remaining_out, row_term);
+  DRS_CUDA(cudaGetLastError());
+  return DRS_OK;
+}
+int launch_merge_runs(const uint64_t* ws, int64_t nq, int nslots, int k, int64_t id_base, float* out_scores,
+                      int64_t* out_ids, uint64_t* bound, int* done, const unsigned int* active_in,
+                      unsigned int* remaining_out, const float* row_term, cudaStream_t st) {
+#define DRS_RUNS(SL) return launch_merge_runs_sl<SL>(ws, nq, nslots, k, id_base, out_scores, out_ids, bound, done, active_in, remaining_out, row_term, st)
+  if (nslots <= 32) DRS_RUNS(1);
+  if (nslots <= 64) DRS_RUNS(2);
+  if (nslots <= 96) DRS_RUNS(3);
+  if (nslots <= 160) DRS_RUNS(5);
+  if (nslots <= 320) DRS_RUNS(10);
+#undef DRS_RUNS
+  return fail(DRS_ERR_UNSUPPORTED, "k > 32 with %d corpus splits per claim (limit 320)", nslots);
+}
+
 }  // namespace
 
 extern "C" {
@@ -332,14 +360,16 @@ int drs_search_workspace_bytes(int64_t nq, int64_t nc, int dim, int k, int dtype
 namespace {
 // one pass: candidates for the k_pass best keys below bound[row] (bound == nullptr: no bound)
 int scan_pass(SearchPlan& p, const void* queries, const void* corpus, int dim, void* workspace, int k_pass,
-              const uint64_t* bound, cudaStream_t st, const float* col_bias = nullptr, size_t extra_bytes = 0) {
+              const uint64_t* bound, cudaStream_t st, const float* col_bias = nullptr, size_t extra_bytes = 0,
+              const unsigned int* active = nullptr) {
+  p.shape.active = active;
   uint64_t* ws = reinterpret_cast<uint64_t*>(static_cast<char*>(workspace) + kWsHeaderBytes + p.bound_bytes + extra_bytes);
   if (p.dtype == DRS_BF16) {
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
     p.shape.round_counter = nullptr;
     if (g_opt.round_barrier && p.grid <= di.num_sms) {   // all CTAs co-resident: the barrier cannot deadlock
-      DRS_CUDA(cudaMemsetAsync(workspace, 0, kWsHeaderBytes, st));
+      DRS_CUDA(cudaMemsetAsync(workspace, 0, kWsRoundBytes, st));
       p.shape.round_counter = static_cast<unsigned int*>(workspace);
     }
     if (p.cg == 1) return p.kcap == 16 ? launch_search_tc<1, 16>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, st)
@@ -381,6 +411,36 @@ int drs_search_select(const void* workspace, int64_t nq, int64_t nc, int dim, in
                            static_cast<cudaStream_t>(stream));
 }
 
+namespace {
+// Scan + select, shared by the dot-product and the squared-L2 searches.
+//   k <= 32: one scan (register lists of 16 or 32 per claim and split) + one select.
+//   k  > 32: adaptive passes (merge.cuh::merge_runs_kernel): all ceil(k/32) passes are enqueued, a pass
+//            whose predecessor left no claim open returns at once on the device (no host sync).
+int run_search(SearchPlan& p, const void* queries, const void* corpus, int dim, int64_t nq, int k, int64_t id_base,
+               float* out_vals, int64_t* out_ids, void* workspace, const float* col_bias, const float* row_term,
+               size_t extra_bytes, cudaStream_t st) {
+  char* base = static_cast<char*>(workspace);
+  const uint64_t* cand = reinterpret_cast<const uint64_t*>(base + kWsHeaderBytes + p.bound_bytes + extra_bytes);
+  if (p.passes == 1) {
+    if (int rc = scan_pass(p, queries, corpus, dim, workspace, k, nullptr, st, col_bias, extra_bytes)) return rc;
+    return launch_merge_keys(cand, nq, num_slots(p.shape) * p.kcap, k, id_base, out_vals, out_ids, k, nullptr, row_term, st);
+  }
+  uint64_t* bound = reinterpret_cast<uint64_t*>(base + kWsHeaderBytes);
+  int* done = reinterpret_cast<int*>(base + kWsHeaderBytes + align256s(static_cast<size_t>(nq) * sizeof(uint64_t)));
+  unsigned int* open_claims = reinterpret_cast<unsigned int*>(base + kWsRoundBytes);  // [pass]
+  DRS_CUDA(cudaMemsetAsync(open_claims, 0, kWsHeaderBytes - kWsRoundBytes, st));
+  DRS_CUDA(cudaMemsetAsync(bound, 0xFF, static_cast<size_t>(nq) * sizeof(uint64_t), st));
+  DRS_CUDA(cudaMemsetAsync(done, 0, static_cast<size_t>(nq) * sizeof(int), st));
+  for (int pass = 0; pass < p.passes; ++pass) {
+    const unsigned int* active = pass ? open_claims + (pass - 1) : nullptr;
+    if (int rc = scan_pass(p, queries, corpus, dim, workspace, 32, pass ? bound : nullptr, st, col_bias, extra_bytes, active)) return rc;
+    if (int rc = launch_merge_runs(cand, nq, num_slots(p.shape), k, id_base, out_vals, out_ids, bound, done, active,
+                                   open_claims + pass, row_term, st)) return rc;
+  }
+  return DRS_OK;
+}
+}  // namespace
+
 int drs_search(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,
                int64_t id_base, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
                void* stream) {
@@ -388,16 +448,16 @@ int drs_search(const void* queries, int64_t nq, const void* corpus, int64_t nc, 
   SearchPlan p;
   if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
   if (int rc = check_search_args(p, queries, corpus, workspace, workspace_bytes)) return rc;
+  return run_search(p, queries, corpus, dim, nq, k, id_base, out_scores, out_ids, workspace, nullptr, nullptr, 0,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int drs_debug_open_claims(const void* workspace, unsigned int out[8], void* stream) {
+  if (!workspace || !out) return fail(DRS_ERR_INVALID, "null pointer argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  char* base = static_cast<char*>(workspace);
-  uint64_t* bound = p.passes > 1 ? reinterpret_cast<uint64_t*>(base + kWsHeaderBytes) : nullptr;
-  const uint64_t* cand = reinterpret_cast<const uint64_t*>(base + kWsHeaderBytes + p.bound_bytes);
-  for (int pass = 0; pass < p.passes; ++pass) {
-    const int k_pass = std::min(32, k - 32 * pass);
-    if (int rc = scan_pass(p, queries, corpus, dim, workspace, p.passes > 1 ? k_pass : k, pass ? bound : nullptr, st)) return rc;
-    if (int rc = launch_merge_keys(cand, nq, num_slots(p.shape) * p.kcap, p.passes > 1 ? k_pass : k, id_base,
-                                   out_scores + 32 * pass, out_ids + 32 * pass, k, bound, nullptr, st)) return rc;
-  }
+  DRS_CUDA(cudaMemcpyAsync(out, static_cast<const char*>(workspace) + kWsRoundBytes, 8 * sizeof(unsigned int),
+                           cudaMemcpyDeviceToHost, st));
+  DRS_CUDA(cudaStreamSynchronize(st));
   return DRS_OK;
 }
 
@@ -424,11 +484,9 @@ int drs_search_l2(const void* queries, int64_t nq, const void* corpus, int64_t n
   if (int rc = check_search_args(p, queries, corpus, workspace, workspace_bytes)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* base = static_cast<char*>(workspace);
-  // layout: [header | bound | -|c|^2 per corpus row | |x|^2 per query | candidates]
-  uint64_t* bound = p.passes > 1 ? reinterpret_cast<uint64_t*>(base + kWsHeaderBytes) : nullptr;
+  // layout: [header | bound, done | -|c|^2 per corpus row | |x|^2 per query | candidates]
   float* col_bias = reinterpret_cast<float*>(base + kWsHeaderBytes + p.bound_bytes);
   float* row_term = reinterpret_cast<float*>(base + kWsHeaderBytes + p.bound_bytes + align256s(nc * sizeof(float)));
-  const uint64_t* cand = reinterpret_cast<const uint64_t*>(base + kWsHeaderBytes + p.bound_bytes + extra);
   const int bc = static_cast<int>((nc + 7) / 8), bq = static_cast<int>((nq + 7) / 8);
   if (dtype == DRS_BF16) {
     drs::row_sqnorm_kernel<__nv_bfloat16><<<bc, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(corpus), nc, dim, -1.f, col_bias);
@@ -438,14 +496,7 @@ int drs_search_l2(const void* queries, int64_t nq, const void* corpus, int64_t n
     drs::row_sqnorm_kernel<float><<<bq, 256, 0, st>>>(static_cast<const float*>(queries), nq, dim, 1.f, row_term);
   }
   DRS_CUDA(cudaGetLastError());
-  for (int pass = 0; pass < p.passes; ++pass) {
-    const int k_pass = std::min(32, k - 32 * pass);
-    if (int rc = scan_pass(p, queries, corpus, dim, workspace, p.passes > 1 ? k_pass : k, pass ? bound : nullptr, st,
-                           col_bias, extra)) return rc;
-    if (int rc = launch_merge_keys(cand, nq, num_slots(p.shape) * p.kcap, p.passes > 1 ? k_pass : k, id_base,
-                                   out_dist + 32 * pass, out_ids + 32 * pass, k, bound, row_term, st)) return rc;
-  }
-  return DRS_OK;
+  return run_search(p, queries, corpus, dim, nq, k, id_base, out_dist, out_ids, workspace, col_bias, row_term, extra, st);
 }
 
 int drs_merge_shards(const float* scores, const int64_t* ids, int num_shards, int64_t nq, int k, float* out_scores,
@@ -463,5 +514,6 @@ int drs_merge_shards(const float* scores, const int64_t* ids, int num_shards, in
 
 #include "infonce_api.inc"
 #include "contrast_api.inc"
+#include "rerank_api.inc"
 
 }  // extern "C"

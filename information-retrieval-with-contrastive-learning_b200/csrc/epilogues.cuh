@@ -31,6 +31,7 @@ struct TopKEpilogue {
   __device__ __forceinline__ void begin_unit(const Params& p, int row, int, int) {
     list.reset();
     bnd = (p.bound != nullptr && row < p.rows_a) ? p.bound[row] : ~0ull;
+    if (bnd == 0ull) list.thr = INFINITY;  // this claim is complete: nothing is eligible, stay on the fast path
   }
 
   __device__ __forceinline__ void chunk(const Params& p, int row, int col0, const uint32_t (&raw)[32]) {
@@ -83,6 +84,7 @@ struct TopKEpilogue {
       const bool hit = ((mine >> j) & 1u) && (s > list.thr) && (make_key(s, static_cast<uint32_t>(col0 + j)) < bnd);
       list.insert(hit ? s : -INFINITY, static_cast<uint32_t>(col0 + j), p.k);
     }
+    if (bnd == 0ull) list.thr = INFINITY;  // (another lane's candidate brought this lane here)
   }
 
   __device__ __forceinline__ void end_unit(const Params& p, int row, int, int slot) {

@@ -37,6 +37,7 @@ struct GemmShape {
   int b_hint;           // L2 eviction hint for the B (corpus) tiles: 0 normal, 1 evict-first, 2 evict-last
   int stagger_cycles;   // producer start delay per A-tile index (experiment knob)
   unsigned int* round_counter;  // zeroed device counter for the per-round producer barrier, or nullptr
+  const unsigned int* active;   // optional: the whole launch is a no-op when *active == 0 (adaptive k > 32 passes)
 };
 
 template <int CG>
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(GemmCfg<CG>::THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmShape shp, const typename Epi::Params ep) {
   using Cfg = GemmCfg<CG>;
+  if (shp.active != nullptr && *shp.active == 0u) return;  // uniform over the grid: nothing left to rescan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;

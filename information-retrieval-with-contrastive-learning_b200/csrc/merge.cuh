@@ -67,6 +67,84 @@ merge_keys_kernel(const uint64_t* __restrict__ ws, int nq, int ncand, int k, lon
   if (bound_out != nullptr && lane == 0) bound_out[q] = prev;
 }
 
+// k > list capacity (32): ADAPTIVE passes.  Every (claim, slot) list holds the slot's KCAP best
+// eligible keys, sorted descending, so the claim's candidates form `nslots` sorted runs and a
+// k-way merge walks them best-first: each lane owns the heads of up to SL slots, one warp max
+// per pick, the winning lane advances its run.  A full run (KCAP entries) may hide more of its
+// slot below its last key; B = the largest such last key.  Every pick >= B is certainly the next
+// best of the whole corpus (anything hidden is < its run's last key <= B), so picks are emitted
+// while they stay >= B -- at least KCAP per pass, usually all k on the first.  A claim that stops
+// early leaves `bound` = its last pick and `done` = its count; the next pass rescans only keys
+// below the bound and continues.  `remaining[0]` counts the unfinished claims of this pass: the
+// next scan and merge return at once when it is zero.  Claims already complete are skipped.
+template <int SL, int KCAP>
+__global__ void __launch_bounds__(128)
+merge_runs_kernel(const uint64_t* __restrict__ ws, int nq, int nslots, int k, long long id_base,
+                  float* __restrict__ out_scores, long long* __restrict__ out_ids, int ld_out,
+                  uint64_t* __restrict__ bound, int* __restrict__ done, const unsigned int* __restrict__ active_in,
+                  unsigned int* __restrict__ remaining_out, const float* __restrict__ row_term) {
+  if (active_in != nullptr && *active_in == 0u) return;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  int r = done[q];
+  if (r >= k) return;
+  const uint64_t* src = ws + static_cast<size_t>(q) * nslots * KCAP;
+  uint64_t head[SL];
+  int pos[SL];
+  uint64_t hidden = 0ull;  // B
+#pragma unroll
+  for (int i = 0; i < SL; ++i) {
+    const int slot = lane + 32 * i;
+    pos[i] = 0;
+    head[i] = 0ull;
+    if (slot < nslots) {
+      head[i] = src[static_cast<size_t>(slot) * KCAP];
+      const uint64_t last = src[static_cast<size_t>(slot) * KCAP + KCAP - 1];
+      hidden = last > hidden ? last : hidden;
+    }
+  }
+  hidden = warp_max_u64(hidden);
+  uint64_t prev = bound[q];
+  bool exhausted = false;
+  for (; r < k; ++r) {
+    uint64_t mine = 0ull;
+#pragma unroll
+    for (int i = 0; i < SL; ++i) mine = head[i] > mine ? head[i] : mine;
+    const uint64_t best = warp_max_u64(mine);
+    if (best == 0ull) { exhausted = hidden == 0ull; break; }
+    if (best < hidden) break;  // a hidden key could outrank it: the next pass continues below `prev`
+    if (mine == best) {        // keys are unique: exactly one lane, one run
+#pragma unroll
+      for (int i = 0; i < SL; ++i) {
+        if (head[i] == best) {
+          ++pos[i];
+          head[i] = pos[i] < KCAP ? src[static_cast<size_t>(lane + 32 * i) * KCAP + pos[i]] : 0ull;
+        }
+      }
+    }
+    if (lane == 0) {
+      float sc = key_score(best);
+      if (row_term != nullptr) sc = fmaxf(row_term[q] - sc, 0.f);
+      out_scores[static_cast<size_t>(q) * ld_out + r] = sc;
+      out_ids[static_cast<size_t>(q) * ld_out + r] = static_cast<long long>(key_index(best)) + id_base;
+    }
+    prev = best;
+  }
+  if (exhausted) {  // fewer than k rows exist: pad like the single-pass select
+    for (int rr = r + lane; rr < k; rr += 32) {
+      out_scores[static_cast<size_t>(q) * ld_out + rr] = row_term != nullptr ? INFINITY : -INFINITY;
+      out_ids[static_cast<size_t>(q) * ld_out + rr] = -1ll;
+    }
+    r = k;
+  }
+  if (lane == 0) {
+    done[q] = r;
+    bound[q] = r >= k ? 0ull : prev;  // 0: nothing is eligible any more
+    if (r < k) atomicAdd(remaining_out, 1u);
+  }
+}
+
 // (score, id) pair order: a is better than b
 __device__ __forceinline__ bool pair_better(float sa, long long ia, float sb, long long ib) {
   return (sa > sb) || (sa == sb && ia < ib);

@@ -103,6 +103,20 @@ def search(queries: torch.Tensor, corpus: torch.Tensor, k: int, *, id_base: int 
     return scores, ids
 
 
+def open_claims_per_pass(device=None):
+    """Debug: claims each pass of the last k > 32 search on this device/stream left open (a list of 8
+    counters; all zero = the first pass finished every claim)."""
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    ws = _workspaces.get((dev.index, torch.cuda.current_stream(dev).cuda_stream))
+    if ws is None:
+        raise RuntimeError("no search has run on this device/stream yet")
+    out = (ctypes.c_uint * 8)()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().drs_debug_open_claims(ws.data_ptr(), ctypes.byref(out),
+                                                     torch.cuda.current_stream(dev).cuda_stream))
+    return list(out)
+
+
 def flat_l2_search(x: torch.Tensor, centroids: torch.Tensor, k: int = 1, *, id_base: int = 0):
     """Exact squared-L2 nearest neighbours: what ``faiss.GpuIndexFlatL2.search(x, k)`` returns at
     src/contrastor/utils.py:64-67 (the k-means assignment of ``run_kmeans``).

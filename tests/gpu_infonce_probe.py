@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Perf probe (test tooling): one NCELoss forward+backward at BASELINE configs[3] (4096 x 768) --
+run under `ncu --metrics gpu__time_duration.sum` for the launch list, or plain for the step time."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import drs_b200 as drs  # noqa: E402
+
+
+def main():
+    n, dim = 4096, 768
+    iters = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(1337)
+    q = torch.nn.functional.normalize(torch.randn(n, dim, generator=g, device=dev), dim=1).requires_grad_(True)
+    k = torch.nn.functional.normalize(torch.randn(n, dim, generator=g, device=dev) * 0.5 + q.detach(), dim=1).requires_grad_(True)
+    crit = drs.NCELoss({"temperature": 0.05})
+
+    def step():
+        q.grad = None
+        k.grad = None
+        crit(q, k, None).backward()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"NCELoss fwd+bwd {n}x{dim}: {e0.elapsed_time(e1) / iters:.3f} ms/step")
+    # the same math as separate library calls (cuBLAS GEMM + ATen softmax-CE), for scale
+    f = torch.cat([q.detach(), k.detach()]).requires_grad_(True)
+
+    def torch_step():
+        f.grad = None
+        s = (f @ f.T) / 0.05
+        s = s.masked_fill(torch.eye(2 * n, dtype=torch.bool, device=dev), float("-inf"))
+        tgt = (torch.arange(2 * n, device=dev) + n) % (2 * n)
+        (torch.nn.functional.cross_entropy(s, tgt, reduction="sum") / 2).backward()
+
+    for _ in range(3):
+        torch_step()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        torch_step()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"torch fp32 matmul + cross_entropy (closed form) {n}x{dim}: {e0.elapsed_time(e1) / iters:.3f} ms/step")
+
+
+if __name__ == "__main__":
+    main()

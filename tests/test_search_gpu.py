@@ -76,8 +76,9 @@ def test_fp32_exact_parity(nq, nc, dim, k):
                                                (torch.float32, 50, 20000, 64, 100), (torch.bfloat16, 40, 700, 64, 256),
                                                (torch.bfloat16, 16, 90, 64, 64)])
 def test_large_k_multi_pass_is_exact(dtype, nq, nc, dim, k):
-    """BASELINE config 4's top-100: k > 32 runs ceil(k/32) passes, each continuing strictly below
-    the previous pass's last pick; must equal the oracle like a single pass (incl. k > Nc)."""
+    """BASELINE config 4's top-100: k > 32 is served by adaptive passes (picks are emitted only while
+    no split's full 32-entry list can hide a better row; open claims are rescanned below their last
+    pick); must equal the oracle like a single pass (incl. k > Nc)."""
     q, c = _data(nq, nc, dim, dtype, planted=True)
     c[nc // 2] = c[5]
     c[nc - 1] = c[5]                                              # ties that straddle pass boundaries
@@ -88,6 +89,34 @@ def test_large_k_multi_pass_is_exact(dtype, nq, nc, dim, k):
     assert i.shape[1] == min(k, nc)
     assert i[0, :3].cpu().tolist() == [5, nc // 2, nc - 1]
     assert all(len(set(r)) == i.shape[1] for r in i.cpu().tolist())
+
+
+def test_large_k_adaptive_passes_one_pass_when_spread_more_when_clustered():
+    """The pass count adapts to the data and the result stays exact either way.
+    Spread neighbours (random corpus): the first pass closes every claim.  Clustered neighbours (a
+    wiki page's sentences are adjacent rows): 90 near-duplicates of the claim inside ONE corpus split
+    overflow its 32-entry list, the claim stays open and later passes finish it."""
+    from importlib import import_module
+    retrieval = import_module(drs_b200.__name__ + ".retrieval")
+    nq, nc, dim, k = 130, 60000, 128, 100
+    q, c = _data(nq, nc, dim, torch.bfloat16, planted=True)
+    s, i = drs_b200.search(q, c, k)
+    _check(q, c, k, s, i, score_rtol=2e-2, gap=1e-4)
+    assert retrieval.open_claims_per_pass()[:4] == [0, 0, 0, 0]
+    g = torch.Generator(device=DEV).manual_seed(7)
+    cf = c.float()
+    base = 1000                                                     # rows 1000..1089: inside one 256-row tile
+    cf[base:base + 90] = _unit(q[3].float()[None, :] + 0.02 * torch.randn(90, dim, generator=g, device=DEV))
+    c2 = cf.to(torch.bfloat16)
+    s, i = drs_b200.search(q, c2, k)
+    ri = _check(q, c2, k, s, i, score_rtol=2e-2, gap=1e-4)
+    opened = retrieval.open_claims_per_pass()
+    assert opened[0] >= 1 and opened[3] == 0, opened
+    assert set(i[3, :90].cpu().tolist()) == set(range(base, base + 90)) == set(ri[3, :90].tolist())
+    d, li = drs_b200.flat_l2_search(q.float(), c2.float(), k)        # same machinery behind the L2 epilogue
+    rd, rli = dense_topk.flat_l2_search(q.float().cpu(), c2.float().cpu(), k)
+    torch.testing.assert_close(d.cpu(), rd, rtol=1e-4, atol=1e-4)
+    assert set(li[3, :90].cpu().tolist()) == set(range(base, base + 90))
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
