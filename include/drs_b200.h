@@ -108,6 +108,26 @@ int drs_rerank(const void* queries, int64_t nq, const void* corpus, int64_t nc, 
 int drs_pair_scores(const void* a, const void* b, int64_t n, int dim, int dtype, float* out, void* stream);
 
 /*
+ * Per-document sentence-pair similarity, a whole batch of documents per call.
+ * Replaces: the body of get_docs_sents_similarity, preprocessing/build_docs_sentence_similarity.py:48-66 --
+ * sklearn cosine_similarity(doc_tfidf, doc_tfidf) (:50), the strict-upper-triangle walk (:59-63; a
+ * one-sentence document yields the single pair (0,0), :54-57) and the stable descending sort (:65).
+ *   indptr [num_sentences+1] int64, indices [nnz] int32 (sorted within a row), data [nnz] float64:
+ *       the CSR rows `vectorizer.transform(doc)` (:49) yields, stacked over all documents (device)
+ *   doc_offsets  [num_docs+1] int64: sentence range of each document (device)
+ *   pair_offsets [num_docs+1] int64: output range of each document = prefix sum of n(n-1)/2
+ *       (1 for n == 1, 0 for n == 0) (device)
+ *   out_i, out_j [total_pairs] int32, out_score [total_pairs] float64: per document, pairs by score
+ *       descending, equal scores in (i, j) lexicographic order (device)
+ * float64 throughout, operation order = the reference's: results are bit-identical to it.
+ */
+int drs_doc_pairs_workspace_bytes(int64_t nnz, int64_t total_pairs, size_t* bytes);
+int drs_doc_sentence_pairs(const int64_t* indptr, const int32_t* indices, const double* data, int64_t num_sentences,
+                           const int64_t* doc_offsets, int64_t num_docs, const int64_t* pair_offsets,
+                           int64_t total_pairs, int64_t nnz, int32_t* out_i, int32_t* out_j, double* out_score,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Merge the per-shard top-k lists of a row-sharded corpus (after the all-gather):
  *   scores device [num_shards, nq, k], ids device [num_shards, nq, k] (id < 0 = empty slot)
  *   -> out_scores / out_ids device [nq, k], ordered by (score desc, id asc).

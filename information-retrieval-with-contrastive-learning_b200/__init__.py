@@ -14,10 +14,13 @@ Everything computes in hand-written sm_100a CUDA behind the C ABI of include/drs
 from . import _lib, build
 from ._lib import get_option, set_option
 from .loss import InfoNCE, NCELoss, info_nce_loss, proto_nce_loss
-from .retrieval import (DenseIndex, FlatL2Index, ShardedDenseIndex, all_gather_topk, flat_l2_search, merge_shards, search,
-                        shard_bounds)
+from .pairs import doc_sentence_pairs_arrays, docs_sentence_pairs, get_docs_sents_similarity
+from .store import load_dense_index, save_dense_index
+from .retrieval import (DenseDocRanker, DenseIndex, FlatL2Index, ShardedDenseIndex, all_gather_topk, flat_l2_search, merge_shards,
+                        paired_scores, rerank, search, shard_bounds)
 
 __all__ = [
-    "search", "flat_l2_search", "FlatL2Index", "merge_shards", "DenseIndex", "ShardedDenseIndex", "all_gather_topk", "shard_bounds",
+    "search", "rerank", "paired_scores", "flat_l2_search", "FlatL2Index", "merge_shards", "DenseIndex", "ShardedDenseIndex", "all_gather_topk", "shard_bounds",
+    "DenseDocRanker", "save_dense_index", "load_dense_index", "docs_sentence_pairs", "doc_sentence_pairs_arrays", "get_docs_sents_similarity",
     "NCELoss", "InfoNCE", "info_nce_loss", "proto_nce_loss", "set_option", "get_option", "build",
 ]

@@ -15,6 +15,7 @@
 #include "gemm_tc.cuh"
 #include "infonce.cuh"
 #include "merge.cuh"
+#include "pairs.cuh"
 #include "rerank.cuh"
 
 namespace {
@@ -160,6 +161,9 @@ struct SearchPlan {
   int grid;        // CTAs
   drs::GemmShape shape;
   size_t bound_bytes;
+  size_t cand_bytes;
+  size_t pad_bytes;   // bf16: zero-padded copy of the claims when nq is not a multiple of the A tile (see scan_pass)
+  int64_t a_rows;     // rows of the A operand as the tensor map sees it (nq rounded up when padded)
   size_t ws_bytes;
 };
 
@@ -193,17 +197,31 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
   }
   // k > 32: per claim a continuation bound (u64) and the count of picks already emitted (int)
   p->bound_bytes = p->passes > 1 ? align256s(static_cast<size_t>(nq) * sizeof(uint64_t)) + align256s(static_cast<size_t>(nq) * sizeof(int)) : 0;
-  p->ws_bytes = kWsHeaderBytes + p->bound_bytes + static_cast<size_t>(nq) * num_slots(p->shape) * p->kcap * sizeof(uint64_t);
+  p->cand_bytes = align256s(static_cast<size_t>(nq) * num_slots(p->shape) * p->kcap * sizeof(uint64_t));
+  p->pad_bytes = 0;
+  p->a_rows = nq;
+  if (dtype == DRS_BF16) {
+    // TMA boxes that hang over the end of the claims matrix are zero-filled correctly but SLOWLY (measured:
+    // 1 claim in a 128-row box streams the corpus at 4.7 TB/s, the same claim zero-padded in memory at
+    // 6.7 TB/s), and with the round barrier one slow A tile holds every cluster back.  Stage a padded copy.
+    const int64_t tile = 128 * p->cg;
+    const int64_t padded = (nq + tile - 1) / tile * tile;
+    if (padded != nq) {
+      p->a_rows = padded;
+      p->pad_bytes = align256s(static_cast<size_t>(padded) * dim * 2);
+    }
+  }
+  p->ws_bytes = kWsHeaderBytes + p->bound_bytes + p->cand_bytes + p->pad_bytes;
   return DRS_OK;
 }
 
 // ------------------------------------------------------------------ generic GEMM launchers
 template <int CG, class Epi>
 int launch_gemm_tc(const void* a, const void* b, int kdim, const drs::GemmShape& shp, int grid,
-                   const typename Epi::Params& ep, cudaStream_t st) {
+                   const typename Epi::Params& ep, cudaStream_t st, int64_t a_rows_alloc = 0) {
   using Cfg = drs::GemmCfg<CG>;
   CUtensorMap ta, tb;
-  if (int rc = make_tmap_bf16(&ta, a, shp.rows_a, kdim, Cfg::BM)) return rc;
+  if (int rc = make_tmap_bf16(&ta, a, a_rows_alloc > 0 ? a_rows_alloc : shp.rows_a, kdim, Cfg::BM)) return rc;
   if (int rc = make_tmap_bf16(&tb, b, shp.rows_b, kdim, Cfg::BN_CTA)) return rc;
   auto kern = drs::gemm_nt_tc_kernel<CG, Epi>;
   DRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -245,11 +263,11 @@ int launch_search_tc(const SearchPlan& p, const void* queries, const void* corpu
   if (col_bias != nullptr) {
     using Epi = drs::TopKEpilogue<KCAP, true>;
     typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, col_bias, 2.0f};
-    return launch_gemm_tc<CG, Epi>(queries, corpus, dim, p.shape, p.grid, ep, st);
+    return launch_gemm_tc<CG, Epi>(queries, corpus, dim, p.shape, p.grid, ep, st, p.a_rows);
   }
   using Epi = drs::TopKEpilogue<KCAP>;
   typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, nullptr, 1.0f};
-  return launch_gemm_tc<CG, Epi>(queries, corpus, dim, p.shape, p.grid, ep, st);
+  return launch_gemm_tc<CG, Epi>(queries, corpus, dim, p.shape, p.grid, ep, st, p.a_rows);
 }
 
 template <int KCAP>
@@ -367,6 +385,13 @@ int scan_pass(SearchPlan& p, const void* queries, const void* corpus, int dim, v
   if (p.dtype == DRS_BF16) {
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
+    if (p.pad_bytes) {  // zero-padded staging copy of the claims (plan_search explains why)
+      char* pad = reinterpret_cast<char*>(ws) + p.cand_bytes;
+      const size_t live = static_cast<size_t>(p.shape.rows_a) * dim * 2;
+      DRS_CUDA(cudaMemcpyAsync(pad, queries, live, cudaMemcpyDeviceToDevice, st));
+      DRS_CUDA(cudaMemsetAsync(pad + live, 0, static_cast<size_t>(p.a_rows) * dim * 2 - live, st));
+      queries = pad;
+    }
     p.shape.round_counter = nullptr;
     if (g_opt.round_barrier && p.grid <= di.num_sms) {   // all CTAs co-resident: the barrier cannot deadlock
       DRS_CUDA(cudaMemsetAsync(workspace, 0, kWsRoundBytes, st));
@@ -515,5 +540,6 @@ int drs_merge_shards(const float* scores, const int64_t* ids, int num_shards, in
 #include "infonce_api.inc"
 #include "contrast_api.inc"
 #include "rerank_api.inc"
+#include "pairs_api.inc"
 
 }  // extern "C"

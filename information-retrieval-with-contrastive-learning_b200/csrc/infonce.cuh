@@ -16,6 +16,14 @@ namespace drs {
 static constexpr float kLog2e = 1.4426950408889634f;
 static constexpr float kLn2 = 0.6931471805599453f;
 
+// 2^x on the MUFU pipe, one instruction (exp2f() wraps it in range fix-ups that double the epilogue cost;
+// the arguments here are y - max <= 0 or y - lse: flushing denormal results to zero is harmless).
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ------------------------------------------------------------------------- forward: row LSE partials
 // Per (row, slot): running max m and l = sum 2^(y - m) over the slot's columns (log2 domain).
 //   pos_mode 0: no positive, nothing masked           (queue operand, contrastive_loss.py:32,:79)
@@ -51,6 +59,33 @@ struct LseEpilogue {
       posj = pc - col0;
     } else if (p.pos_mode == 2) {
       posj = row - col0;
+    }
+    if (p.col_scale == nullptr && valid >= 32) {
+      // Fast path (all but ~2 of a row's 256 chunks): no masked column, no positive, one temperature.
+      // max over the raw scores (scale > 0 keeps the order), then one FFMA + one MUFU per score.
+      const bool special = (static_cast<unsigned>(diag) < 32u) || (static_cast<unsigned>(posj) < 32u);
+      if (!__any_sync(0xffffffffu, special)) {
+        float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          c0 = fmaxf(c0, __uint_as_float(v[j + 0]));
+          c1 = fmaxf(c1, __uint_as_float(v[j + 1]));
+          c2 = fmaxf(c2, __uint_as_float(v[j + 2]));
+          c3 = fmaxf(c3, __uint_as_float(v[j + 3]));
+        }
+        const float m_new = fmaxf(m, fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)) * p.scale_log2);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          a0 += fast_ex2(fmaf(__uint_as_float(v[j + 0]), p.scale_log2, -m_new));
+          a1 += fast_ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -m_new));
+          a2 += fast_ex2(fmaf(__uint_as_float(v[j + 2]), p.scale_log2, -m_new));
+          a3 += fast_ex2(fmaf(__uint_as_float(v[j + 3]), p.scale_log2, -m_new));
+        }
+        l = l * fast_ex2(m - m_new) + ((a0 + a1) + (a2 + a3));
+        m = m_new;
+        return;
+      }
     }
     float y[32];
     float cmax = -INFINITY;
@@ -108,16 +143,73 @@ struct GradLogitEpilogue {
     li2 = (p.mode == 1) ? p.lse2[r + p.n_rows_q] : 0.f;
     c = p.coef * __ldg(p.grad);
   }
+  static __device__ __forceinline__ void store32(OutT* dst, const float (&h)[32]) {
+    if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(h[j + 0], h[j + 1]);
+        __nv_bfloat162 t1 = __floats2bfloat162_rn(h[j + 2], h[j + 3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(h[j + 4], h[j + 5]);
+        __nv_bfloat162 t3 = __floats2bfloat162_rn(h[j + 6], h[j + 7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&t0);
+        pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2);
+        pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(dst + j) = pk;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
+    }
+  }
+
   __device__ __forceinline__ void chunk(const Params& p, int row, int col0, const uint32_t (&v)[32]) {
-    if (row >= p.rows_a) return;
     const int valid = min(32, p.rows_b - col0);
     if (valid <= 0) return;
+    const bool live = row < p.rows_a;
     const int diag = row - col0;
     int posj = -1;
     if (p.mode == 0) {
       const int pc = row < p.half ? row + p.half : row - p.half;
       posj = pc - col0;
     }
+    OutT* dst_fast = p.out + static_cast<long long>(row) * p.ld_out + col0;
+    if (p.mode <= 2 && p.col_scale == nullptr && valid == 32 && ((p.ld_out * sizeof(OutT)) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+      // Fast path: a full, aligned chunk with one temperature and (mode 0) neither the diagonal nor the
+      // positive in it -- per score one FFMA + one MUFU per softmax term, nothing else.
+      const bool special = live && p.mode == 0 && ((static_cast<unsigned>(diag) < 32u) || (static_cast<unsigned>(posj) < 32u));
+      if (!__any_sync(0xffffffffu, special)) {
+        if (!live) return;
+        float h[32];
+        if (p.mode == 0) {
+          const float4* lp = reinterpret_cast<const float4*>(p.lse2 + col0);  // col0 % 32 == 0: 16-byte aligned
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 lj = __ldg(lp + j4);
+            const float ljs[4] = {lj.x, lj.y, lj.z, lj.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float s = __uint_as_float(v[4 * j4 + t]);
+              h[4 * j4 + t] = c * (fast_ex2(fmaf(s, p.scale_log2, -li)) + fast_ex2(fmaf(s, p.scale_log2, -ljs[t])));
+            }
+          }
+        } else if (p.mode == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float s = __uint_as_float(v[j]);
+            h[j] = c * (fast_ex2(fmaf(s, p.scale_log2, -li)) + fast_ex2(fmaf(s, p.scale_log2, -li2)));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) h[j] = c * fast_ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -li));
+        }
+        store32(dst_fast, h);
+        return;
+      }
+    }
+    if (!live) return;
     float h[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -219,68 +311,104 @@ struct StoreEpilogue {
 };
 
 // ------------------------------------------------------------------------- helper kernels
-// F = cat(q, k) in fp32 and/or bf16, plus bf16 F^T ([dim][2N]) for the K-major B operand of dF = H F.
-__global__ void infonce_pack_kernel(const float* __restrict__ q, const float* __restrict__ k, int n, int dim,
-                                    float* __restrict__ f32, __nv_bfloat16* __restrict__ bf, __nv_bfloat16* __restrict__ bf_t) {
-  const long long total = 2ll * n * dim;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / dim), d = static_cast<int>(i - static_cast<long long>(r) * dim);
-    const float x = r < n ? q[static_cast<long long>(r) * dim + d] : k[static_cast<long long>(r - n) * dim + d];
-    if (f32) f32[i] = x;
-    if (bf) bf[i] = __float2bfloat16_rn(x);
-    if (bf_t) bf_t[static_cast<long long>(d) * (2ll * n) + r] = __float2bfloat16_rn(x);
-  }
-}
-// queue [dim][K] fp32 -> transposed [K][dim] (fp32 and/or bf16) and a bf16 copy in the original layout
-__global__ void infonce_queue_pack_kernel(const float* __restrict__ queue, int dim, long long klen,
-                                          float* __restrict__ qt32, __nv_bfloat16* __restrict__ qt_bf,
-                                          __nv_bfloat16* __restrict__ q_bf) {
-  const long long total = klen * dim;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long c = i / dim;
-    const int d = static_cast<int>(i - c * dim);
-    const float x = queue[static_cast<long long>(d) * klen + c];
-    if (qt32) qt32[i] = x;
-    if (qt_bf) qt_bf[i] = __float2bfloat16_rn(x);
-    if (q_bf) q_bf[static_cast<long long>(d) * klen + c] = __float2bfloat16_rn(x);
+// Operand staging through 32 x 32 shared-memory tiles, so that the row-major copy AND the transposed
+// copy are both written with full 128-byte lines (a plain "one thread per element" transpose writes
+// 2-byte elements 16 KB apart and took 60 us for the 8192 x 768 operand; this takes ~10).
+//   src: [R][C] fp32 row-major; rows [0, split) come from s0, rows [split, R) from s1 (cat(q, k), :61)
+//   any of: o32 [R][C] fp32, obf [R][C] bf16, o32_t [C][R] fp32, obf_t [C][R] bf16
+__global__ void __launch_bounds__(256)
+pack_transpose_kernel(const float* __restrict__ s0, const float* __restrict__ s1, long long split, long long R, long long C,
+                      float* __restrict__ o32, __nv_bfloat16* __restrict__ obf, float* __restrict__ o32_t,
+                      __nv_bfloat16* __restrict__ obf_t) {
+  __shared__ float tile[32][33];
+  const long long tiles_c = (C + 31) / 32, tiles_r = (R + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (long long t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const long long r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long r = r0 + ty + 8 * i, c = c0 + tx;
+      float x = 0.f;
+      if (r < R && c < C) {
+        x = r < split ? s0[r * C + c] : s1[(r - split) * C + c];
+        if (o32) o32[r * C + c] = x;
+        if (obf) obf[r * C + c] = __float2bfloat16_rn(x);
+      }
+      tile[ty + 8 * i][tx] = x;
+    }
+    __syncthreads();
+    if (o32_t || obf_t) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long c = c0 + ty + 8 * i, r = r0 + tx;  // consecutive threads -> consecutive r
+        if (r < R && c < C) {
+          const float x = tile[tx][ty + 8 * i];
+          if (o32_t) o32_t[c * R + r] = x;
+          if (obf_t) obf_t[c * R + r] = __float2bfloat16_rn(x);
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
-// Combine the split partials (and the queue partials of row i mod N) into lse (natural log),
-// lse2 (log2 domain) and the loss = sum_i (lse_i - pos_i) / 2   (contrastive_loss.py:92).
-// One block; deterministic tree reduction.
+// (m, l) pairs in the log2 domain: l_a 2^m_a + l_b 2^m_b
+__device__ __forceinline__ void lse_combine(float& m, float& l, float m2, float l2) {
+  const float mn = fmaxf(m, m2);
+  if (mn == -INFINITY) return;  // both empty
+  l = l * exp2f(m - mn) + l2 * exp2f(m2 - mn);
+  m = mn;
+}
+
+// Row log-sum-exp from the slot partials: one WARP per row, lanes stride over the slots (coalesced;
+// the old one-block kernel walked 74 partials per thread 592 bytes apart and took 540 us at 2N = 8192).
+//   part   [rows][slots]          in-batch / prototype partials
+//   part_q [rows_q][slots_q]      optional queue partials of row (i mod rows_q)  (the .repeat(2,1), :80)
+//   include_pos: the positive logit pos[i] is an extra column (MoCo form, :30-36)
+__global__ void __launch_bounds__(256)
+lse_rows_kernel(const float2* __restrict__ part, int slots, const float2* __restrict__ part_q, int slots_q, int rows_q,
+                const float* __restrict__ pos, int include_pos, int rows, float* __restrict__ lse,
+                float* __restrict__ lse2) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float m = -INFINITY, l = 0.f;
+  if (include_pos && lane == 0) {
+    m = pos[row] * kLog2e;
+    l = 1.f;
+  }
+  for (int s = lane; s < slots; s += 32) {
+    const float2 p = part[static_cast<size_t>(row) * slots + s];
+    lse_combine(m, l, p.x, p.y);
+  }
+  if (part_q != nullptr) {
+    const int r = row % rows_q;
+    for (int s = lane; s < slots_q; s += 32) {
+      const float2 p = part_q[static_cast<size_t>(r) * slots_q + s];
+      lse_combine(m, l, p.x, p.y);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const float l2 = __shfl_xor_sync(0xffffffffu, l, o);
+    lse_combine(m, l, m2, l2);
+  }
+  if (lane == 0) {
+    const float v = m + log2f(l);
+    lse2[row] = v;
+    lse[row] = v * kLn2;
+  }
+}
+
+// loss = scale * sum_i (lse_i - pos_i)   (contrastive_loss.py:92 sum/2; :24,:42 mean).  One block, fixed
+// reduction tree: deterministic.
 __global__ void __launch_bounds__(1024)
-infonce_finalize_kernel(const float2* __restrict__ part, int splits, const float2* __restrict__ part_q, int splits_q,
-                        const float* __restrict__ pos, int two_n, int n, float* __restrict__ lse,
-                        float* __restrict__ lse2, float* __restrict__ loss) {
+loss_sum_kernel(const float* __restrict__ lse, const float* __restrict__ pos, int rows, float scale,
+                float* __restrict__ loss) {
   __shared__ float red[32];
   float local = 0.f;
-  for (int i = threadIdx.x; i < two_n; i += blockDim.x) {
-    float m = -INFINITY, l = 0.f;
-    for (int s = 0; s < splits; ++s) {
-      const float2 p = part[static_cast<size_t>(i) * splits + s];
-      if (p.x == -INFINITY) continue;
-      const float mn = fmaxf(m, p.x);
-      l = l * exp2f(m - mn) + p.y * exp2f(p.x - mn);
-      m = mn;
-    }
-    if (part_q) {
-      const int r = i < n ? i : i - n;
-      for (int s = 0; s < splits_q; ++s) {
-        const float2 p = part_q[static_cast<size_t>(r) * splits_q + s];
-        if (p.x == -INFINITY) continue;
-        const float mn = fmaxf(m, p.x);
-        l = l * exp2f(m - mn) + p.y * exp2f(p.x - mn);
-        m = mn;
-      }
-    }
-    const float l2 = m + log2f(l);
-    lse2[i] = l2;
-    lse[i] = l2 * kLn2;
-    local += l2 * kLn2 - pos[i];
-  }
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) local += lse[i] - pos[i];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
@@ -289,21 +417,7 @@ infonce_finalize_kernel(const float2* __restrict__ part, int splits, const float
     float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) loss[0] = 0.5f * v;
-  }
-}
-
-// rows [R][dim] fp32 -> bf16 copy and/or bf16 transpose [dim][R]  (ProtoNCE prototypes, MoCo q)
-__global__ void pack_rows_kernel(const float* __restrict__ src, long long rows, int dim,
-                                 __nv_bfloat16* __restrict__ bf, __nv_bfloat16* __restrict__ bf_t) {
-  const long long total = rows * dim;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / dim;
-    const int d = static_cast<int>(i - r * dim);
-    const __nv_bfloat16 x = __float2bfloat16_rn(src[i]);
-    if (bf) bf[i] = x;
-    if (bf_t) bf_t[static_cast<long long>(d) * rows + r] = x;
+    if (threadIdx.x == 0) loss[0] = scale * v;
   }
 }
 
@@ -318,44 +432,6 @@ __global__ void rowdot_kernel(const float* __restrict__ q, const float* __restri
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) pos[row] = acc * inv_t;
-}
-
-// Generic finalize: lse_i from the slot partials (plus the positive logit itself when it is not
-// among the GEMM columns, MoCo form), loss = loss_scale * sum_i (lse_i - pos_i).  One block.
-__global__ void __launch_bounds__(1024)
-lse_finalize_kernel(const float2* __restrict__ part, int slots, const float* __restrict__ pos, int include_pos,
-                    int rows, float loss_scale, float* __restrict__ lse, float* __restrict__ lse2,
-                    float* __restrict__ loss) {
-  __shared__ float red[32];
-  float local = 0.f;
-  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
-    float m = -INFINITY, l = 0.f;
-    if (include_pos) {
-      m = pos[i] * kLog2e;
-      l = 1.f;
-    }
-    for (int s = 0; s < slots; ++s) {
-      const float2 p = part[static_cast<size_t>(i) * slots + s];
-      if (p.x == -INFINITY) continue;
-      const float mn = fmaxf(m, p.x);
-      l = l * exp2f(m - mn) + p.y * exp2f(p.x - mn);
-      m = mn;
-    }
-    const float l2 = m + log2f(l);
-    lse2[i] = l2;
-    lse[i] = l2 * kLn2;
-    local += l2 * kLn2 - pos[i];
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) loss[0] = loss_scale * v;
-  }
 }
 
 // MoCo backward, positive column (contrastive_loss.py:30,:42): a_i = g (p0_i - 1) inv_T / N with

@@ -194,6 +194,74 @@ class FlatL2Index:
         return d.cpu().numpy(), i.cpu().numpy()
 
 
+def rerank(queries: torch.Tensor, corpus: torch.Tensor, cand_ids: torch.Tensor, k: int):
+    """Score each claim against its OWN candidate rows and keep the best k -- the dense stage of the
+    report's "TF-IDF top-100 -> contrastive re-rank -> top-15" (report.pdf section 3.2), to be placed at
+    src/evaluation.py:105-116 after the sparse candidates of documents_filtering (:57-83).
+
+    queries [nq, D], corpus [Nc, D] (CUDA, same dtype: bf16 or fp32); cand_ids [nq, m] integer corpus
+    rows, negative (or >= Nc) entries are padding.  Returns (scores fp32 [nq, k'], ids int64 [nq, k'])
+    with k' = min(k, m), sorted descending, ties -> lower row, a row listed twice reported once,
+    (-inf, -1) where a claim has fewer than k' valid candidates."""
+    _check_matrix("queries", queries)
+    _check_matrix("corpus", corpus)
+    if queries.device != corpus.device:
+        raise RuntimeError(f"queries ({queries.device}) and corpus ({corpus.device}) must be on the same device")
+    if queries.shape[1] != corpus.shape[1]:
+        raise ValueError(f"dimension mismatch: queries {tuple(queries.shape)} vs corpus {tuple(corpus.shape)}")
+    if not isinstance(cand_ids, torch.Tensor) or cand_ids.dim() != 2 or cand_ids.shape[0] != queries.shape[0]:
+        raise ValueError("cand_ids must be a [nq, m] integer tensor")
+    if cand_ids.dtype.is_floating_point:
+        raise TypeError("cand_ids must hold integer row numbers")
+    if k <= 0:
+        raise ValueError(f"k must be positive, got {k}")
+    if queries.dtype != corpus.dtype:
+        queries = queries.to(corpus.dtype)
+    nq, dim = queries.shape
+    m = cand_ids.shape[1]
+    kk = min(int(k), m)
+    dev = queries.device
+    scores = torch.empty(nq, kk, dtype=torch.float32, device=dev)
+    ids = torch.empty(nq, kk, dtype=torch.int64, device=dev)
+    if nq == 0 or kk == 0:
+        return scores, ids
+    if corpus.shape[0] == 0:
+        return scores.fill_(float("-inf")), ids.fill_(-1)
+    queries = queries.contiguous()
+    corpus = corpus.contiguous()
+    cand = cand_ids.to(device=dev, dtype=torch.int64).contiguous()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.load().drs_rerank(queries.data_ptr(), nq, corpus.data_ptr(), corpus.shape[0], dim,
+                                          _DTYPES[corpus.dtype], cand.data_ptr(), m, kk, scores.data_ptr(),
+                                          ids.data_ptr(), stream))
+    return scores, ids
+
+
+def paired_scores(a: torch.Tensor, b: torch.Tensor):
+    """``(clm_vec * evdn_vec).sum(dim=-1)`` of the commented dense evaluation (src/evaluation.py:112,115):
+    row-wise dot products of two [n, D] CUDA matrices -> fp32 [n] (the caller takes ``.mean()``)."""
+    _check_matrix("a", a)
+    _check_matrix("b", b)
+    if a.shape != b.shape:
+        raise ValueError(f"shape mismatch: {tuple(a.shape)} vs {tuple(b.shape)}")
+    if a.device != b.device:
+        raise RuntimeError("a and b must be on the same device")
+    if a.dtype != b.dtype:
+        a, b = a.float(), b.float()
+    n, dim = a.shape
+    out = torch.empty(n, dtype=torch.float32, device=a.device)
+    if n == 0:
+        return out
+    if dim == 0:
+        return out.zero_()
+    a, b = a.contiguous(), b.contiguous()
+    with torch.cuda.device(a.device):
+        stream = torch.cuda.current_stream(a.device).cuda_stream
+        _lib.check(_lib.load().drs_pair_scores(a.data_ptr(), b.data_ptr(), n, dim, _DTYPES[a.dtype], out.data_ptr(), stream))
+    return out
+
+
 def merge_shards(scores: torch.Tensor, ids: torch.Tensor):
     """[g, nq, k] per-shard lists (id < 0 = empty) -> [nq, k] by (score desc, id asc)."""
     if scores.dim() != 3 or scores.shape != ids.shape:
@@ -256,6 +324,28 @@ class DenseIndex:
         q = queries.to(device=self.device, dtype=self.embeddings.dtype, non_blocking=True)
         return search(q, self.embeddings, k, id_base=self.id_base, profile=profile)
 
+    def rerank(self, queries: torch.Tensor, cand_ids, k: int = 15):
+        """Dense re-rank of per-claim candidate rows (report.pdf section 3.2: sparse top-100 -> dense top-15).
+        ``cand_ids`` [nq, m]: GLOBAL row numbers (this shard's ``id_base`` is subtracted; rows outside the
+        shard and negative entries are ignored).  Returns device (scores, global ids)."""
+        q = queries.to(device=self.device, dtype=self.embeddings.dtype, non_blocking=True)
+        cand = torch.as_tensor(cand_ids).to(device=self.device, dtype=torch.int64)
+        if self.id_base:
+            cand = torch.where(cand >= 0, cand - self.id_base, cand)
+        s, i = rerank(q, self.embeddings, cand, k)
+        if self.id_base:
+            i = torch.where(i >= 0, i + self.id_base, i)
+        return s, i
+
+    def save(self, filename: str, metadata: Optional[dict] = None):
+        """Write this corpus to an index file (store.save_dense_index); the doc-id map travels as
+        ``metadata['doc_dict']`` like the reference's (retriever/utils.py:21-29)."""
+        from .store import save_dense_index
+        meta = dict(metadata or {})
+        if self.doc_dict is not None:
+            meta.setdefault("doc_dict", self.doc_dict)
+        save_dense_index(filename, self.embeddings, meta, dtype=self.embeddings.dtype)
+
     def closest_docs(self, query: torch.Tensor, k: int = 1):
         """tfidf_doc_ranker.py:60-75 -- one query vector [D] -> (list of doc ids, np.ndarray scores)."""
         res = self.batch_closest_docs(query.reshape(1, -1), k)
@@ -272,6 +362,38 @@ class DenseIndex:
             keep = i_row >= 0
             out.append(([self.get_doc_id(int(i) - self.id_base) for i in i_row[keep]], s_row[keep]))
         return out
+
+
+class DenseDocRanker(DenseIndex):
+    """``TfidfDocRanker`` with dense vectors: built from an index FILE (tfidf_doc_ranker.py:33-50 loads
+    ``tfidf_path``; here ``store.save_dense_index`` wrote it) and queried with TEXT -- ``encoder`` turns a
+    list of strings into [n, D] embeddings, i.e. ``lambda texts: model.ctx2vec(texts, device)``
+    (src/contrastor/contrastive_module.py:96-100), the call the commented block at
+    src/evaluation.py:110-111 makes.  Tensors are accepted too (then no encoder is needed)."""
+
+    def __init__(self, index_path: str, encoder=None, *, device=None, rank: int = 0, world_size: int = 1, strict: bool = True):
+        from .store import load_dense_index
+        index, meta = load_dense_index(index_path, device=device, rank=rank, world_size=world_size)
+        self.__dict__.update(index.__dict__)
+        self.metadata = meta
+        self.encoder = encoder
+        self.strict = strict
+
+    def text2vec(self, queries):
+        if self.encoder is None:
+            raise RuntimeError("DenseDocRanker was built without an encoder: pass embeddings, or encoder=model.ctx2vec")
+        with torch.no_grad():
+            return self.encoder(list(queries))
+
+    def closest_docs(self, query, k: int = 1):
+        if isinstance(query, str):
+            query = self.text2vec([query])
+        return super().closest_docs(query, k)
+
+    def batch_closest_docs(self, queries, k: int = 1, num_workers=None):
+        if not isinstance(queries, torch.Tensor):
+            queries = self.text2vec(queries)
+        return super().batch_closest_docs(queries, k, num_workers)
 
 
 class ShardedDenseIndex:

@@ -156,3 +156,33 @@ def flat_l2_search(x: torch.Tensor, centroids: torch.Tensor, k: int = 1):
     d = (xf * xf).sum(1, keepdim=True) + (cf * cf).sum(1)[None, :] - 2.0 * xf @ cf.T
     vals, idx = torch.sort(d, dim=1, descending=False, stable=True)
     return vals[:, :k].float().contiguous(), idx[:, :k].contiguous()
+
+
+def rerank(queries: torch.Tensor, corpus: torch.Tensor, cand_ids: torch.Tensor, k: int):
+    """Candidate-restricted scoring: report.pdf section 3.2 ("TF-IDF top-100 -> re-rank -> top-15"),
+    intended at src/evaluation.py:105-116.  Per claim: gather its candidate rows, dot products in fp32
+    (the idiom of evaluation.py:112), select like closest_docs (tfidf_doc_ranker.py:67-73) with the
+    lower-row tie rule.  Negative / out-of-range ids are padding; a row listed twice counts once.
+    Returns (scores fp32 [nq, k'], ids int64 [nq, k']), k' = min(k, m), padded with (-inf, -1)."""
+    q = queries.float()
+    c = corpus.float()
+    nq, m = cand_ids.shape
+    kk = min(k, m)
+    out_s = torch.full((nq, kk), float("-inf"), dtype=torch.float32)
+    out_i = torch.full((nq, kk), -1, dtype=torch.int64)
+    for r in range(nq):
+        ids = [int(v) for v in cand_ids[r].tolist() if 0 <= int(v) < c.shape[0]]
+        ids = sorted(set(ids))                       # ascending row: a stable descending sort keeps ties low-row first
+        if not ids:
+            continue
+        idt = torch.tensor(ids, dtype=torch.int64)
+        sc = (c[idt] * q[r][None, :]).sum(dim=-1)    # (clm_vec * evdn_vec).sum(dim=-1)
+        order = torch.argsort(sc, descending=True, stable=True)[:kk]
+        out_s[r, : order.numel()] = sc[order]
+        out_i[r, : order.numel()] = idt[order]
+    return out_s, out_i
+
+
+def paired_scores(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """src/evaluation.py:112 -- ``(clm_vec * evdn_vec).sum(dim=-1)`` (fp32)."""
+    return (a.float() * b.float()).sum(dim=-1)

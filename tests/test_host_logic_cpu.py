@@ -118,3 +118,14 @@ def test_sharded_exchange_world2_gloo(tmp_path):
         ok, first, second = np.load(tmp_path / f"ok{r}.npy")
         assert ok == 1
         assert (first, second) == (3, nc - 1)        # tie broken by the lower global id across shards
+
+
+def test_pair_builder_host_logic_and_no_cpu_path():
+    """n(n-1)/2 pairs per document, 1 for a one-sentence document (build_docs_sentence_similarity.py:54-57),
+    0 for an empty one; without a CUDA device the builder refuses instead of computing on the CPU."""
+    from importlib import import_module
+    pairs = import_module(drs_b200.__name__ + ".pairs")
+    assert pairs.pair_counts(np.array([0, 1, 2, 3, 10])).tolist() == [0, 1, 1, 3, 45]
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            drs_b200.docs_sentence_pairs([np.eye(3)])

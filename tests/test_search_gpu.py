@@ -289,3 +289,69 @@ def test_flat_l2_search_kmeans_assignment(dtype, n, nc, dim, k):
     assert index.ntotal == nc
     dd, ii = index.search(x[:50].cpu().float().numpy(), 1)
     assert ii.shape == (50, 1) and ii.dtype == np.int64 and [int(v) for v in ii[:, 0]] == lab[:50].cpu().tolist()
+
+
+@pytest.mark.parametrize("dtype,nq,nc,dim,m,k", [(torch.bfloat16, 200, 30000, 768, 100, 15), (torch.float32, 64, 5000, 128, 100, 15),
+                                                 (torch.float32, 9, 300, 50, 7, 7), (torch.bfloat16, 33, 999, 100, 40, 5)])
+def test_rerank_sparse_candidates_then_dense_topk(dtype, nq, nc, dim, m, k):
+    """report.pdf section 3.2: sparse top-100 candidates -> dense re-rank -> top-15 (site: evaluation.py:105-116)."""
+    q, c = _data(nq, nc, dim, dtype, planted=True)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    cand = torch.randint(0, nc, (nq, m), generator=g, device=DEV)
+    cand[0, 1] = cand[0, 0]                                   # duplicate candidate -> reported once
+    cand[1, m // 2:] = -1                                     # ragged list (padding)
+    if nq > 2:
+        cand[2, :] = -1                                       # no candidates at all
+    s, i = drs_b200.rerank(q, c, cand, k)
+    rs, ri = dense_topk.rerank(q.cpu(), c.cpu(), cand.cpu(), k)
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    fin = torch.isfinite(rs)
+    assert torch.equal(torch.isfinite(s.cpu()), fin)
+    torch.testing.assert_close(s.cpu()[fin], rs[fin], rtol=tol, atol=tol * 1e-1)
+    gap_next = torch.cat([rs[:, :-1] - rs[:, 1:], torch.full((nq, 1), 1e30)], dim=1)
+    gap_prev = torch.cat([torch.full((nq, 1), 1e30), rs[:, :-1] - rs[:, 1:]], dim=1)
+    strict = fin & (gap_next > 1e-4) & (gap_prev > 1e-4)
+    assert torch.equal(i.cpu()[strict], ri[strict])
+    assert torch.equal(i.cpu()[~fin], ri[~fin])               # -1 padding in the same places
+    # a DenseIndex shard with an id_base returns global ids
+    idx = drs_b200.DenseIndex(c, dtype=dtype, id_base=1000)
+    s2, i2 = idx.rerank(q, torch.where(cand >= 0, cand + 1000, cand), k)
+    assert torch.equal(s2, s) and torch.equal(i2, torch.where(i >= 0, i + 1000, i))
+
+
+@pytest.mark.parametrize("dtype,n,dim", [(torch.float32, 1000, 128), (torch.bfloat16, 513, 768), (torch.float32, 7, 50)])
+def test_paired_scores_matches_reference_expression(dtype, n, dim):
+    """src/evaluation.py:112: `(clm_vec * evdn_vec).sum(dim=-1).mean()`."""
+    q, c = _data(n, n, dim, dtype, planted=True)
+    out = drs_b200.paired_scores(q, c)
+    ref = dense_topk.paired_scores(q.cpu(), c.cpu())
+    tol = 1e-5 if dtype == torch.float32 else 1e-4
+    torch.testing.assert_close(out.cpu(), ref, rtol=tol, atol=tol)
+    assert abs(out.mean().item() - ref.mean().item()) < 1e-5
+
+
+def test_index_file_round_trip_and_text_ranker(tmp_path):
+    """save -> load (whole and as the 2 shards of a 2-rank job) -> same search results; DenseDocRanker is
+    TfidfDocRanker's surface (path in, text queries in, (doc_ids, scores) out) with a stand-in encoder."""
+    q, c = _data(50, 3000, 128, torch.bfloat16, planted=True)
+    ids = [f"Page_{i}" for i in range(3000)]
+    idx = drs_b200.DenseIndex(c, ids)
+    path = str(tmp_path / "corpus.drsidx")
+    idx.save(path, {"note": "test"})
+    s0, i0 = idx.search(q, 10)
+    loaded, meta = drs_b200.load_dense_index(path)
+    assert meta["note"] == "test" and torch.equal(loaded.embeddings, idx.embeddings)
+    s1, i1 = loaded.search(q, 10)
+    assert torch.equal(s0, s1) and torch.equal(i0, i1)
+    parts = [drs_b200.load_dense_index(path, rank=r, world_size=2)[0] for r in range(2)]
+    assert [p.id_base for p in parts] == [0, 1500]
+    ss, ii = zip(*[p.search(q, 10) for p in parts])
+    ms, mi = drs_b200.merge_shards(torch.stack(ss), torch.stack(ii))
+    assert torch.equal(ms, s0) and torch.equal(mi, i0)
+    assert parts[1].closest_docs(q[0], 3)[0][0].startswith("Page_")
+    table = {f"claim {n}": q[n] for n in range(50)}
+    ranker = drs_b200.DenseDocRanker(path, encoder=lambda texts: torch.stack([table[t] for t in texts]))
+    docs, scores = ranker.closest_docs("claim 3", 5)
+    assert docs == [ids[j] for j in i0[3, :5].tolist()] and scores.dtype == np.float64
+    batch = ranker.batch_closest_docs(["claim 1", "claim 2"], 2)
+    assert [b[0][0] for b in batch] == [ids[i0[1, 0].item()], ids[i0[2, 0].item()]]
