@@ -57,6 +57,7 @@ struct Options {
   int b_hint = 0;
   int stagger_cycles = 0;
   int round_barrier = 1;
+  int seed_thresholds = 1;
 } g_opt;
 
 struct DeviceInfo {
@@ -162,6 +163,8 @@ struct SearchPlan {
   drs::GemmShape shape;
   size_t bound_bytes;
   size_t cand_bytes;
+  size_t seed_bytes;  // threshold seeds [nq][seed_slots] (epilogues.cuh), zeroed before every scan
+  int seed_slots;     // ceil(k / kcap): that many disjoint ranges with >= kcap rows above a score bound k rows
   size_t pad_bytes;   // bf16: zero-padded copy of the claims when nq is not a multiple of the A tile (see scan_pass)
   int64_t a_rows;     // rows of the A operand as the tensor map sees it (nq rounded up when padded)
   size_t ws_bytes;
@@ -211,7 +214,9 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
       p->pad_bytes = align256s(static_cast<size_t>(padded) * dim * 2);
     }
   }
-  p->ws_bytes = kWsHeaderBytes + p->bound_bytes + p->cand_bytes + p->pad_bytes;
+  p->seed_slots = p->passes;   // == ceil(k / 32) when k > 32, else 1
+  p->seed_bytes = align256s(static_cast<size_t>(nq) * p->seed_slots * sizeof(uint32_t));
+  p->ws_bytes = kWsHeaderBytes + p->bound_bytes + p->cand_bytes + p->pad_bytes + p->seed_bytes;
   return DRS_OK;
 }
 
@@ -259,28 +264,28 @@ int launch_gemm_simt(const float* a, long long lda, const float* b, long long ld
 
 template <int CG, int KCAP>
 int launch_search_tc(const SearchPlan& p, const void* queries, const void* corpus, int dim, uint64_t* ws, int k_pass,
-                     const uint64_t* bound, const float* col_bias, cudaStream_t st) {
+                     const uint64_t* bound, const float* col_bias, uint32_t* seeds, cudaStream_t st) {
   if (col_bias != nullptr) {
     using Epi = drs::TopKEpilogue<KCAP, true>;
-    typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, col_bias, 2.0f};
+    typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, col_bias, 2.0f, seeds, p.seed_slots};
     return launch_gemm_tc<CG, Epi>(queries, corpus, dim, p.shape, p.grid, ep, st, p.a_rows);
   }
   using Epi = drs::TopKEpilogue<KCAP>;
-  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, nullptr, 1.0f};
+  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, nullptr, 1.0f, seeds, p.seed_slots};
   return launch_gemm_tc<CG, Epi>(queries, corpus, dim, p.shape, p.grid, ep, st, p.a_rows);
 }
 
 template <int KCAP>
 int launch_search_f32(const SearchPlan& p, const void* queries, const void* corpus, int dim, uint64_t* ws, int k_pass,
-                      const uint64_t* bound, const float* col_bias, cudaStream_t st) {
+                      const uint64_t* bound, const float* col_bias, uint32_t* seeds, cudaStream_t st) {
   if (col_bias != nullptr) {
     using Epi = drs::TopKEpilogue<KCAP, true>;
-    typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, col_bias, 2.0f};
+    typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, col_bias, 2.0f, seeds, p.seed_slots};
     return launch_gemm_simt<Epi, false>(static_cast<const float*>(queries), dim, static_cast<const float*>(corpus),
                                         dim, dim, p.shape, p.grid, ep, st);
   }
   using Epi = drs::TopKEpilogue<KCAP>;
-  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, nullptr, 1.0f};
+  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, nullptr, 1.0f, seeds, p.seed_slots};
   return launch_gemm_simt<Epi, false>(static_cast<const float*>(queries), dim, static_cast<const float*>(corpus), dim,
                                       dim, p.shape, p.grid, ep, st);
 }
@@ -350,6 +355,7 @@ int drs_set_option(const char* name, int value) {
   else if (!strcmp(name, "tune.b_hint")) g_opt.b_hint = value;
   else if (!strcmp(name, "tune.stagger_cycles")) g_opt.stagger_cycles = value;
   else if (!strcmp(name, "tune.round_barrier")) g_opt.round_barrier = value;
+  else if (!strcmp(name, "tune.seed_thresholds")) g_opt.seed_thresholds = value;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;
 }
@@ -363,6 +369,7 @@ int drs_get_option(const char* name, int* value) {
   else if (!strcmp(name, "tune.b_hint")) *value = g_opt.b_hint;
   else if (!strcmp(name, "tune.stagger_cycles")) *value = g_opt.stagger_cycles;
   else if (!strcmp(name, "tune.round_barrier")) *value = g_opt.round_barrier;
+  else if (!strcmp(name, "tune.seed_thresholds")) *value = g_opt.seed_thresholds;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;
 }
@@ -381,6 +388,12 @@ int scan_pass(SearchPlan& p, const void* queries, const void* corpus, int dim, v
               const uint64_t* bound, cudaStream_t st, const float* col_bias = nullptr, size_t extra_bytes = 0,
               const unsigned int* active = nullptr) {
   p.shape.active = active;
+  uint32_t* seeds = nullptr;
+  if (g_opt.seed_thresholds && p.shape.num_splits > 1) {
+    seeds = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + kWsHeaderBytes + p.bound_bytes + extra_bytes +
+                                        p.cand_bytes + p.pad_bytes);
+    DRS_CUDA(cudaMemsetAsync(seeds, 0, p.seed_bytes, st));
+  }
   uint64_t* ws = reinterpret_cast<uint64_t*>(static_cast<char*>(workspace) + kWsHeaderBytes + p.bound_bytes + extra_bytes);
   if (p.dtype == DRS_BF16) {
     DeviceInfo di;
@@ -397,13 +410,13 @@ int scan_pass(SearchPlan& p, const void* queries, const void* corpus, int dim, v
       DRS_CUDA(cudaMemsetAsync(workspace, 0, kWsRoundBytes, st));
       p.shape.round_counter = static_cast<unsigned int*>(workspace);
     }
-    if (p.cg == 1) return p.kcap == 16 ? launch_search_tc<1, 16>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, st)
-                                       : launch_search_tc<1, 32>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, st);
-    return p.kcap == 16 ? launch_search_tc<2, 16>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, st)
-                        : launch_search_tc<2, 32>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, st);
+    if (p.cg == 1) return p.kcap == 16 ? launch_search_tc<1, 16>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, seeds, st)
+                                       : launch_search_tc<1, 32>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, seeds, st);
+    return p.kcap == 16 ? launch_search_tc<2, 16>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, seeds, st)
+                        : launch_search_tc<2, 32>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, seeds, st);
   }
-  return p.kcap == 16 ? launch_search_f32<16>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, st)
-                      : launch_search_f32<32>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, st);
+  return p.kcap == 16 ? launch_search_f32<16>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, seeds, st)
+                      : launch_search_f32<32>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, seeds, st);
 }
 int check_search_args(const SearchPlan& p, const void* queries, const void* corpus, void* workspace,
                       size_t workspace_bytes) {

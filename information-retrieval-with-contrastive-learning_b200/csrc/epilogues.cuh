@@ -24,14 +24,31 @@ struct TopKEpilogue {
                             // (k > KCAP is served in passes: each pass continues below the last pick)
     const float* col_bias;  // BIASED: ranked value = score_scale * dot + col_bias[col]
     float score_scale;      //   (squared-L2 search: 2 x.c - |c|^2, src/contrastor/utils.py:64-67)
+    // Threshold seeding across units.  seeds: [rows_a][seed_slots] ordered-uint32 scores, zeroed before the
+    // scan.  A unit that ends with a full list publishes its k-th best; the seed_slots largest values published
+    // for a claim come from seed_slots DISJOINT corpus ranges, each holding >= k rows that score at least that
+    // much, so with seed_slots * k >= (the k the caller wants) the smallest of them is a lower bound on the
+    // final k-th best score: later units of the claim start from it instead of from -inf and stay on the
+    // fast path (a fresh list needs ~k ln(n/k) inserts to warm up, and one lane's insert stalls its warp).
+    // Any stale or missing seed is merely a weaker bound -- the result is exact either way.
+    uint32_t* seeds;
+    int seed_slots;
   };
   TopKList<KCAP> list;
   uint64_t bnd;
 
   __device__ __forceinline__ void begin_unit(const Params& p, int row, int, int) {
-    list.reset();
+    float floor = -INFINITY;
     bnd = (p.bound != nullptr && row < p.rows_a) ? p.bound[row] : ~0ull;
-    if (bnd == 0ull) list.thr = INFINITY;  // this claim is complete: nothing is eligible, stay on the fast path
+    if (bnd == 0ull) {
+      floor = INFINITY;  // this claim is complete: nothing is eligible, stay on the fast path
+    } else if (p.seeds != nullptr && row < p.rows_a) {
+      uint32_t lo = 0xFFFFFFFFu;
+      for (int j = 0; j < p.seed_slots; ++j) lo = min(lo, __ldcg(p.seeds + static_cast<size_t>(row) * p.seed_slots + j));
+      // strictly below the bound, so that rows TYING it (with a lower index) still enter
+      if (lo != 0u) floor = ordered_to_float(lo - 1u);
+    }
+    list.reset(floor);
   }
 
   __device__ __forceinline__ void chunk(const Params& p, int row, int col0, const uint32_t (&raw)[32]) {
@@ -84,7 +101,6 @@ struct TopKEpilogue {
       const bool hit = ((mine >> j) & 1u) && (s > list.thr) && (make_key(s, static_cast<uint32_t>(col0 + j)) < bnd);
       list.insert(hit ? s : -INFINITY, static_cast<uint32_t>(col0 + j), p.k);
     }
-    if (bnd == 0ull) list.thr = INFINITY;  // (another lane's candidate brought this lane here)
   }
 
   __device__ __forceinline__ void end_unit(const Params& p, int row, int, int slot) {
@@ -92,6 +108,16 @@ struct TopKEpilogue {
     uint64_t* dst = p.ws + (static_cast<size_t>(row) * p.num_slots + slot) * KCAP;
 #pragma unroll
     for (int j = 0; j < KCAP; ++j) dst[j] = list.key(j);
+    if (p.seeds != nullptr && list.kth > -INFINITY) {
+      // keep the seed_slots largest published values: each atomicMax leaves the larger in place and carries
+      // the smaller down, which conserves the multiset {slots, carry} under any interleaving
+      uint32_t v = float_to_ordered(list.kth);
+      uint32_t* a = p.seeds + static_cast<size_t>(row) * p.seed_slots;
+      for (int j = 0; j < p.seed_slots && v != 0u; ++j) {
+        const uint32_t old = atomicMax(a + j, v);
+        v = min(old, v);
+      }
+    }
   }
 };
 

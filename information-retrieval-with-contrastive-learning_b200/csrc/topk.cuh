@@ -35,15 +35,19 @@ template <int KCAP>
 struct TopKList {
   float sc[KCAP];
   uint32_t ix[KCAP];
-  float thr;
+  float thr;    // a candidate must beat this: max(k-th best of the list, floor)
+  float kth;    // the list's own k-th best score (-inf while it holds fewer than k)
+  float floor;  // externally known lower bound: scores <= floor cannot be among the final k
 
-  __device__ __forceinline__ void reset() {
+  __device__ __forceinline__ void reset(float floor_ = -INFINITY) {
 #pragma unroll
     for (int j = 0; j < KCAP; ++j) {
       sc[j] = -INFINITY;
       ix[j] = 0xFFFFFFFFu;
     }
-    thr = -INFINITY;
+    kth = -INFINITY;
+    floor = floor_;
+    thr = floor_;
   }
   // `s` = -inf makes this a no-op, which is how lanes without a candidate ride along
   __device__ __forceinline__ void insert(float s, uint32_t idx, int k) {
@@ -60,7 +64,8 @@ struct TopKList {
     float t = sc[0];
 #pragma unroll
     for (int j = 1; j < KCAP; ++j) t = (j < k) ? sc[j] : t;
-    thr = t;  // sc[k-1]
+    kth = t;  // sc[k-1]
+    thr = fmaxf(t, floor);
   }
   __device__ __forceinline__ uint64_t key(int j) const {
     return sc[j] == -INFINITY ? 0ull : make_key(sc[j], ix[j]);

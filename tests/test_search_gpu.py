@@ -355,3 +355,30 @@ def test_index_file_round_trip_and_text_ranker(tmp_path):
     assert docs == [ids[j] for j in i0[3, :5].tolist()] and scores.dtype == np.float64
     batch = ranker.batch_closest_docs(["claim 1", "claim 2"], 2)
     assert [b[0][0] for b in batch] == [ids[i0[1, 0].item()], ids[i0[2, 0].item()]]
+
+
+@pytest.mark.parametrize("dtype,k", [(torch.bfloat16, 10), (torch.bfloat16, 100), (torch.float32, 10)])
+def test_threshold_seeding_keeps_ties_and_matches_unseeded(dtype, k):
+    """Units that finish early publish their k-th best score and later units of the same claim start
+    from it (epilogues.cuh).  With few CTAs the corpus splits run one after another, so the seeds are
+    live; exact duplicates of the best row sit in a LATE split (published first to nobody) and in an
+    EARLY one: the answer must be the lowest row numbers, identical to the run without seeding."""
+    nq, nc, dim = 40, 74 * 1024, 128
+    q, c = _data(nq, nc, dim, dtype, planted=True)
+    dup = c[70000].clone()
+    c[60000:60012] = dup
+    c[100:112] = dup
+    c[70000] = c[5]
+    q[0] = dup
+    try:
+        drs_b200.set_option("search.num_ctas", 4)
+        s1, i1 = drs_b200.search(q, c, k)
+        drs_b200.set_option("tune.seed_thresholds", 0)
+        s0, i0 = drs_b200.search(q, c, k)
+    finally:
+        drs_b200.set_option("search.num_ctas", 0)
+        drs_b200.set_option("tune.seed_thresholds", 1)
+    assert torch.equal(i1, i0) and torch.equal(s1, s0)
+    assert i1[0, :10].cpu().tolist() == list(range(100, 110))
+    tol = (1e-5, 2e-6) if dtype == torch.float32 else (2e-2, 1e-4)
+    _check(q, c, k, s1, i1, score_rtol=tol[0], gap=tol[1])
