@@ -229,7 +229,8 @@ def run_b200(args):
     queries = torch.nn.functional.normalize(torch.randn(nq, dim, generator=gq, device=dev), dim=1).bfloat16()
     queries_host = queries.cpu().pin_memory()
     index = drs_b200.ShardedDenseIndex(shard, nc, device=dev) if world > 1 else drs_b200.DenseIndex(shard, device=dev)
-    launches_per_step = 2 + (1 if world > 1 else 0)         # scan + select (+ shard merge)
+    # scan + select on one GPU; sharded: scan + the fused select/exchange/merge kernel (p2p), or scan + select + merge (nccl)
+    launches_per_step = 2 if (world == 1 or index.exchange == "p2p") else 3
 
     def barrier():
         if world > 1:
@@ -340,7 +341,9 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16 in, fp32 accumulate", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {nq} claims x {nc} x {dim} bf16, top-{k}",
-                       "parallelism": f"corpus row-sharded x{world}, all-gather + on-GPU merge",
+                       "parallelism": (f"corpus row-sharded x{world}, " + ("fused select + NVLink peer-memory exchange + merge kernel"
+                                                                           if world > 1 and index.exchange == "p2p" else
+                                                                           "NCCL all-gather + on-GPU merge") if world > 1 else "one GPU, whole corpus resident"),
                        "l2": "corpus shard (>= 4.8 GB) exceeds the 126 MB L2 every step; no flush needed"},
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clk.summary(), "roofline": roofline,
         }

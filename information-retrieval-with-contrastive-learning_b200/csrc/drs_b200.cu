@@ -11,6 +11,7 @@
 
 #include "../../include/drs_b200.h"
 #include "epilogues.cuh"
+#include "exchange.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "infonce.cuh"
@@ -307,6 +308,23 @@ int launch_merge_keys(const uint64_t* ws, int64_t nq, int ncand, int k, int64_t 
   return DRS_OK;
 }
 
+// single-pass select: k-way merge of the sorted per-slot runs; unsorted re-scan only beyond 320 slots
+int launch_select(const uint64_t* ws, int64_t nq, int nslots, int kcap, int k, int64_t id_base, float* out_scores,
+                  int64_t* out_ids, const float* row_term, cudaStream_t st) {
+  const int blocks = static_cast<int>((nq + 3) / 4);
+  long long* ids = reinterpret_cast<long long*>(out_ids);
+#define DRS_SEL(SL) drs::select_runs_kernel<SL><<<blocks, 128, 0, st>>>(ws, (int)nq, nslots, kcap, k, id_base, out_scores, ids, row_term)
+  if (nslots <= 32) DRS_SEL(1);
+  else if (nslots <= 64) DRS_SEL(2);
+  else if (nslots <= 96) DRS_SEL(3);
+  else if (nslots <= 160) DRS_SEL(5);
+  else if (nslots <= 320) DRS_SEL(10);
+  else return launch_merge_keys(ws, nq, nslots * kcap, k, id_base, out_scores, out_ids, k, nullptr, row_term, st);
+#undef DRS_SEL
+  DRS_CUDA(cudaGetLastError());
+  return DRS_OK;
+}
+
 template <int SL>
 int launch_merge_runs_sl(const uint64_t* ws, int64_t nq, int nslots, int k, int64_t id_base, float* out_scores,
                          int64_t* out_ids, uint64_t* bound, int* done, const unsigned int* active_in,
@@ -444,9 +462,8 @@ int drs_search_select(const void* workspace, int64_t nq, int64_t nc, int dim, in
   SearchPlan p;
   if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
   if (p.passes > 1) return fail(DRS_ERR_UNSUPPORTED, "drs_search_scan/select serve k <= 32; use drs_search for k = %d", k);
-  return launch_merge_keys(reinterpret_cast<const uint64_t*>(static_cast<const char*>(workspace) + kWsHeaderBytes), nq,
-                           num_slots(p.shape) * p.kcap, k, id_base, out_scores, out_ids, k, nullptr, nullptr,
-                           static_cast<cudaStream_t>(stream));
+  return launch_select(reinterpret_cast<const uint64_t*>(static_cast<const char*>(workspace) + kWsHeaderBytes), nq,
+                       num_slots(p.shape), p.kcap, k, id_base, out_scores, out_ids, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 namespace {
@@ -461,7 +478,7 @@ int run_search(SearchPlan& p, const void* queries, const void* corpus, int dim, 
   const uint64_t* cand = reinterpret_cast<const uint64_t*>(base + kWsHeaderBytes + p.bound_bytes + extra_bytes);
   if (p.passes == 1) {
     if (int rc = scan_pass(p, queries, corpus, dim, workspace, k, nullptr, st, col_bias, extra_bytes)) return rc;
-    return launch_merge_keys(cand, nq, num_slots(p.shape) * p.kcap, k, id_base, out_vals, out_ids, k, nullptr, row_term, st);
+    return launch_select(cand, nq, num_slots(p.shape), p.kcap, k, id_base, out_vals, out_ids, row_term, st);
   }
   uint64_t* bound = reinterpret_cast<uint64_t*>(base + kWsHeaderBytes);
   int* done = reinterpret_cast<int*>(base + kWsHeaderBytes + align256s(static_cast<size_t>(nq) * sizeof(uint64_t)));
@@ -554,5 +571,6 @@ int drs_merge_shards(const float* scores, const int64_t* ids, int num_shards, in
 #include "contrast_api.inc"
 #include "rerank_api.inc"
 #include "pairs_api.inc"
+#include "exchange_api.inc"
 
 }  // extern "C"

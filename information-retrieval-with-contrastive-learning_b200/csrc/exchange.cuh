@@ -1,0 +1,163 @@
+// Fused select + exchange + merge for a row-sharded corpus: ONE kernel after the scan, over NVLink
+// peer memory ("all-gather of per-shard top-k lists followed by an on-GPU merge").
+//
+// The unfused form is four launches and two collectives per search: select (per-split candidate
+// keys -> this shard's top-k), ncclAllGather of the scores, ncclAllGather of the ids, merge.  The
+// payload is tiny (10 000 claims x top-10 x 12 B = 1.2 MB per rank), so the step is pure launch and
+// collective latency -- negligible next to a 40 ms tensor-bound scan, but 10 % of a step in the
+// small-batch, HBM-bound regime where a shard is streamed in under a millisecond.
+//
+// Here every rank runs the same persistent kernel.  For each block of 32 claims:
+//   1. select: one warp per claim reduces the candidate keys to the shard's top-k (pick r lands in
+//      lane r) and stores the list straight into slot [rank] of EVERY peer's gather buffer -- plain
+//      st.global through the NVLink peer mapping, 128-byte lines;
+//   2. publish: __syncthreads, fence.sys, then st.release.sys of the call's epoch into flag
+//      [block][rank] of every peer;
+//   3. wait: ld.acquire.sys until all `world` flags of this claim block show the epoch -- the lists
+//      of this block have arrived from every shard (no global barrier: blocks proceed independently);
+//   4. merge: the warp orders the world * k candidates by (score desc, id asc) and writes the result.
+// Flags carry a monotonically increasing epoch and are never reset, so there is no cleanup pass and
+// a change of batch size between calls is harmless.  The gather buffers are double-buffered by
+// epoch parity: a rank can be at most one call ahead of its slowest peer (it cannot finish call n+1
+// before every peer has published call n+1, i.e. finished reading call n).
+// All CTAs are co-resident (grid <= resident capacity) and every block publishes before it waits,
+// so the spin cannot deadlock; a wait that exceeds a few seconds traps with a hang report.
+#pragma once
+#include "merge.cuh"
+#include "ptx.cuh"
+
+namespace drs {
+
+constexpr int kMaxPeers = 8;
+enum : uint32_t { kTagExchangeWait = 6 };
+
+struct ExchangePeers {
+  float* scores[kMaxPeers];     // rank p's gather buffer: [world][nq][k] fp32   (peer-mapped pointers)
+  long long* ids[kMaxPeers];    //                         [world][nq][k] int64
+  uint32_t* flags[kMaxPeers];   // rank p's flags:         [claim blocks][world]
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int kExchangeRowsPerBlock = 8;  // 8 warps, one claim each
+
+// ws: [nq][nslots][kcap] candidate keys of this shard (the scan's output: sorted runs).  k <= 32.
+// SL: runs per lane of the k-way select (nslots <= 32 * SL); 0 = unsorted re-scan of all candidates per pick.
+template <int SL>
+__global__ void __launch_bounds__(256)
+select_exchange_merge_kernel(const uint64_t* __restrict__ ws, int nq, int nslots, int kcap, int k, long long id_base,
+                             const ExchangePeers peers, int rank, int world, uint32_t epoch,
+                             float* __restrict__ out_scores, long long* __restrict__ out_ids) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_blocks = (nq + kExchangeRowsPerBlock - 1) / kExchangeRowsPerBlock;
+  const size_t slot = static_cast<size_t>(nq) * k;  // one rank's [nq][k] list
+  for (int rb = blockIdx.x; rb < num_blocks; rb += gridDim.x) {
+    const int q = rb * kExchangeRowsPerBlock + warp;
+    // ---- 1. select this shard's top-k and scatter it to every peer
+    if (q < nq) {
+      const uint64_t* src = ws + static_cast<size_t>(q) * nslots * kcap;
+      uint64_t mine = 0ull;
+      if constexpr (SL > 0) {
+        mine = warp_select_runs<SL>(src, nslots, kcap, k, lane);
+      } else {
+        uint64_t prev = ~0ull;
+        for (int r = 0; r < k; ++r) {
+          uint64_t best = 0ull;
+          for (int c = lane; c < nslots * kcap; c += 32) {
+            const uint64_t key = __ldg(src + c);
+            if (key < prev && key > best) best = key;
+          }
+          best = warp_max_u64(best);
+          if (lane == r) mine = best;
+          prev = best;
+        }
+      }
+      if (lane < k) {
+        const float sc = mine ? key_score(mine) : -INFINITY;
+        const long long id = mine ? static_cast<long long>(key_index(mine)) + id_base : -1ll;
+        const size_t off = static_cast<size_t>(rank) * slot + static_cast<size_t>(q) * k + lane;
+        for (int p = 0; p < world; ++p) {
+          peers.scores[p][off] = sc;
+          peers.ids[p][off] = id;
+        }
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // ---- 2. publish (the barrier above ordered the block's stores before this fence)
+      __threadfence_system();
+      if (lane < world) st_release_sys_u32(peers.flags[lane] + static_cast<size_t>(rb) * world + rank, epoch);
+      // ---- 3. wait for this claim block's lists from every shard
+      const uint32_t* fl = peers.flags[rank] + static_cast<size_t>(rb) * world;
+      const long long t0 = clock64();
+      for (;;) {
+        const uint32_t v = lane < world ? ld_acquire_sys_u32(fl + lane) : epoch;
+        if (__all_sync(0xffffffffu, static_cast<int32_t>(v - epoch) >= 0)) break;
+        __nanosleep(200);
+        if (clock64() - t0 > kMbarTimeoutCycles) mbar_hang(kTagExchangeWait, epoch, static_cast<uint32_t>(rb));
+      }
+    }
+    __syncthreads();
+    // ---- 4. merge world * k candidates (L2 reads: peer stores land in this GPU's L2, never in its L1)
+    const float* in_s = peers.scores[rank];
+    const long long* in_i = peers.ids[rank];
+    const int total = world * k;
+    if (q < nq) {
+      float ps = INFINITY;
+      long long pi = -1;
+      // world * k <= 8 * 32 candidates: 8 per lane, read once (id < 0 = empty slot)
+      float cs[kMaxPeers];
+      long long ci[kMaxPeers];
+#pragma unroll
+      for (int u = 0; u < kMaxPeers; ++u) {
+        const int c = lane + 32 * u;
+        ci[u] = -1;
+        cs[u] = -INFINITY;
+        if (c < total) {
+          const int shard = c / k, j = c - shard * k;
+          const size_t off = static_cast<size_t>(shard) * slot + static_cast<size_t>(q) * k + j;
+          ci[u] = __ldcg(in_i + off);
+          cs[u] = __ldcg(in_s + off);
+        }
+      }
+      for (int r = 0; r < k; ++r) {
+        float bs = -INFINITY;
+        long long bi = -1;
+#pragma unroll
+        for (int u = 0; u < kMaxPeers; ++u) {
+          if (ci[u] < 0) continue;
+          if (!pair_better(ps, pi, cs[u], ci[u])) continue;  // not strictly worse than the previous pick
+          if (bi < 0 || pair_better(cs[u], ci[u], bs, bi)) { bs = cs[u]; bi = ci[u]; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+          const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (oi >= 0 && (bi < 0 || pair_better(os, oi, bs, bi))) { bs = os; bi = oi; }
+        }
+        if (lane == 0) {
+          out_scores[static_cast<size_t>(q) * k + r] = bi >= 0 ? bs : -INFINITY;
+          out_ids[static_cast<size_t>(q) * k + r] = bi;
+        }
+        if (bi < 0) {
+          for (int rr = r + 1 + lane; rr < k; rr += 32) {
+            out_scores[static_cast<size_t>(q) * k + rr] = -INFINITY;
+            out_ids[static_cast<size_t>(q) * k + rr] = -1;
+          }
+          break;
+        }
+        ps = bs;
+        pi = bi;
+      }
+    }
+  }
+}
+
+}  // namespace drs

@@ -67,6 +67,58 @@ merge_keys_kernel(const uint64_t* __restrict__ ws, int nq, int ncand, int k, lon
   if (bound_out != nullptr && lane == 0) bound_out[q] = prev;
 }
 
+// The candidates of one claim are `nslots` runs of `kcap` keys, each sorted descending (the register
+// lists of the scan epilogue), so the k best come out of a k-way merge: each lane owns the heads of up
+// to SL runs, one warp max per pick, the winning lane advances its run.  ~SL compares per pick instead
+// of ncand / 32.  Returns pick r in lane r (0 = fewer than r + 1 candidates).  k <= 32.
+template <int SL>
+__device__ __forceinline__ uint64_t warp_select_runs(const uint64_t* __restrict__ src, int nslots, int kcap, int k, int lane) {
+  uint64_t head[SL];
+  int pos[SL];
+#pragma unroll
+  for (int i = 0; i < SL; ++i) {
+    const int slot = lane + 32 * i;
+    pos[i] = 0;
+    head[i] = slot < nslots ? __ldg(src + static_cast<size_t>(slot) * kcap) : 0ull;
+  }
+  uint64_t mine = 0ull;
+  for (int r = 0; r < k; ++r) {
+    uint64_t m = 0ull;
+#pragma unroll
+    for (int i = 0; i < SL; ++i) m = head[i] > m ? head[i] : m;
+    const uint64_t best = warp_max_u64(m);
+    if (best == 0ull) break;
+    if (lane == r) mine = best;
+    if (m == best) {  // keys are unique per claim: exactly one lane, one run
+#pragma unroll
+      for (int i = 0; i < SL; ++i) {
+        if (head[i] == best) {
+          ++pos[i];
+          head[i] = pos[i] < kcap ? __ldg(src + static_cast<size_t>(lane + 32 * i) * kcap + pos[i]) : 0ull;
+        }
+      }
+    }
+  }
+  return mine;
+}
+
+// Final select of a single-pass search (k <= 32) by run merge: one warp per claim.
+template <int SL>
+__global__ void __launch_bounds__(128)
+select_runs_kernel(const uint64_t* __restrict__ ws, int nq, int nslots, int kcap, int k, long long id_base,
+                   float* __restrict__ out_scores, long long* __restrict__ out_ids, const float* __restrict__ row_term) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const uint64_t mine = warp_select_runs<SL>(ws + static_cast<size_t>(q) * nslots * kcap, nslots, kcap, k, lane);
+  if (lane < k) {
+    float sc = mine ? key_score(mine) : -INFINITY;
+    if (row_term != nullptr) sc = mine ? fmaxf(row_term[q] - sc, 0.f) : INFINITY;
+    out_scores[static_cast<size_t>(q) * k + lane] = sc;
+    out_ids[static_cast<size_t>(q) * k + lane] = mine ? static_cast<long long>(key_index(mine)) + id_base : -1ll;
+  }
+}
+
 // k > list capacity (32): ADAPTIVE passes.  Every (claim, slot) list holds the slot's KCAP best
 // eligible keys, sorted descending, so the claim's candidates form `nslots` sorted runs and a
 // k-way merge walks them best-first: each lane owns the heads of up to SL slots, one warp max

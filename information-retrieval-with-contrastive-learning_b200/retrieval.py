@@ -396,17 +396,60 @@ class DenseDocRanker(DenseIndex):
         return super().batch_closest_docs(queries, k, num_workers)
 
 
+class _PeerExchange:
+    """Symmetric (peer-mapped) gather buffers and flags for the fused select + exchange + merge kernel
+    (csrc/exchange.cuh): every rank allocates the same layout and maps every peer's copy over NVLink.
+
+        [ flags: claim blocks x world u32 | parity 0: scores, ids | parity 1: scores, ids ]
+    """
+
+    MAX_NQ = 1 << 17
+
+    def __init__(self, group, device, world, rank, capacity):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank, self.capacity = world, rank, int(capacity)         # capacity: nq * k entries
+        need = ctypes.c_size_t(0)
+        _lib.check(_lib.load().drs_exchange_flag_bytes(self.MAX_NQ, world, ctypes.byref(need)))
+        self.flag_bytes = need.value
+        self.s_bytes = (world * self.capacity * 4 + 255) // 256 * 256
+        self.i_bytes = (world * self.capacity * 8 + 255) // 256 * 256
+        total = self.flag_bytes + 2 * (self.s_bytes + self.i_bytes)
+        self.buf = symm.empty(total, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.handle.barrier()                         # every rank's flags are zero before anyone publishes
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.epoch = 0
+
+    def pointer_arrays(self):
+        """(epoch, scores[world], ids[world], flags[world]) as ctypes arrays for the next call."""
+        self.epoch += 1
+        par = self.epoch & 1
+        base = self.flag_bytes + par * (self.s_bytes + self.i_bytes)
+        arr = ctypes.c_void_p * self.world
+        return (self.epoch, arr(*[p + base for p in self.ptrs]), arr(*[p + base + self.s_bytes for p in self.ptrs]),
+                arr(*self.ptrs))
+
+
 class ShardedDenseIndex:
     """Row-sharded corpus over the ranks of a torch.distributed group (one process per GPU).
 
-    Each rank holds rows ``shard_bounds(N, rank, world)`` and runs the same fused kernel on
-    them; the per-rank (score, global id) lists are all-gathered (NCCL over NVLink on GPUs;
-    any backend works) and merged on the GPU by (score desc, id asc), which makes the result
-    identical to a single-GPU search of the whole corpus.
+    Each rank holds rows ``shard_bounds(N, rank, world)`` and runs the same fused scan kernel on them.
+    The per-rank (score, global id) lists are then exchanged and merged by (score desc, id asc), which
+    makes the result identical to a single-GPU search of the whole corpus.  Two exchanges:
+
+    * ``exchange='p2p'``: ONE kernel per search selects the shard's top-k, stores it into every peer's
+      buffer over NVLink peer memory, waits on per-claim-block flags and merges (csrc/exchange.cuh);
+      needs the NCCL backend's symmetric memory, k <= 32, <= 8 ranks, no empty shard;
+    * ``exchange='nccl'``: select, ``all_gather_into_tensor`` of scores and ids, merge kernel (any backend).
+
+    ``exchange='auto'`` (default) takes 'p2p' when its conditions hold, else 'nccl'.
     """
 
     def __init__(self, local_embeddings: torch.Tensor, total_rows: int, *, group=None, device=None,
-                 dtype: torch.dtype = torch.bfloat16):
+                 dtype: torch.dtype = torch.bfloat16, exchange: str = "auto"):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -415,14 +458,48 @@ class ShardedDenseIndex:
         lo, hi = shard_bounds(total_rows, self.rank, self.world)
         if local_embeddings.shape[0] != hi - lo:
             raise ValueError(f"rank {self.rank} must hold rows [{lo}, {hi}) = {hi - lo} rows, got {local_embeddings.shape[0]}")
+        if exchange not in ("auto", "p2p", "nccl"):
+            raise ValueError("exchange must be 'auto', 'p2p' or 'nccl'")
         self.total_rows = total_rows
         self.local = DenseIndex(local_embeddings, device=device, dtype=dtype, id_base=lo)
+        # the same decision on every rank: it depends only on group-wide facts
+        smallest = min(b - a for a, b in (shard_bounds(total_rows, r, self.world) for r in range(self.world)))
+        p2p_ok = (self.world > 1 and self.world <= 8 and smallest > 0 and self.local.embeddings.is_cuda
+                  and dist.get_backend(group) == "nccl")
+        if exchange == "p2p" and not p2p_ok:
+            raise RuntimeError("exchange='p2p' needs the nccl backend, 2..8 ranks, CUDA shards and no empty shard")
+        self.exchange = "p2p" if (p2p_ok and exchange != "nccl") else "nccl"
+        self._exchange_requested = exchange
+        self._peer = None
+
+    def _peer_exchange(self, entries: int):
+        """The symmetric buffers, (re)allocated collectively -- every rank sees the same `entries`.  Returns
+        None (and switches this index to the NCCL exchange on ALL ranks) if any rank fails to map its peers."""
+        if self._peer is None or self._peer.capacity < entries:
+            cap = max(entries, 1 << 17) if self._peer is None else max(entries, 2 * self._peer.capacity)
+            ok, err = 1, None
+            try:
+                peer = _PeerExchange(self.group, self.local.device, self.world, self.rank, cap)
+            except Exception as e:  # noqa: BLE001  (no peer access, symmetric memory unavailable, ...)
+                ok, err, peer = 0, e, None
+            flag = torch.tensor([ok], device=self.local.device)
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
+            if not int(flag.item()):
+                if self._exchange_requested == "p2p":
+                    raise RuntimeError(f"exchange='p2p': peer memory could not be mapped on every rank ({err})")
+                self.exchange, self._peer = "nccl", None
+                return None
+            self._peer = peer
+        return self._peer
 
     def search(self, queries: torch.Tensor, k: int = 1, profile: Optional[list] = None):
         kk = min(int(k), self.total_rows)
+        nq = queries.shape[0]
+        if self.exchange == "p2p" and 0 < kk <= 32 and 0 < nq <= _PeerExchange.MAX_NQ:
+            if self._peer_exchange(nq * kk) is not None:
+                return self._search_p2p(queries, kk, profile)
         s, i = (self.local.search(queries, min(kk, max(self.local.num_docs, 1)), profile=profile)
                 if self.local.num_docs else (None, None))
-        nq = queries.shape[0]
         dev = self.local.device
         # fixed-size slots so every rank contributes the same number of bytes
         slot_s = torch.full((nq, kk), float("-inf"), dtype=torch.float32, device=dev)
@@ -434,6 +511,38 @@ class ShardedDenseIndex:
             return slot_s, slot_i
         all_s, all_i = all_gather_topk(slot_s, slot_i, self.group)
         return merge_shards(all_s, all_i)
+
+    def _search_p2p(self, queries: torch.Tensor, kk: int, profile: Optional[list]):
+        loc = self.local
+        dev = loc.device
+        q = queries.to(device=dev, dtype=loc.embeddings.dtype, non_blocking=True).contiguous()
+        _check_matrix("queries", q)
+        if q.shape[1] != loc.embeddings.shape[1]:
+            raise ValueError(f"dimension mismatch: queries {tuple(q.shape)} vs corpus {tuple(loc.embeddings.shape)}")
+        nq, dim = q.shape
+        nc = loc.num_docs
+        peer = self._peer
+        lib = _lib.load()
+        dt = _DTYPES[loc.embeddings.dtype]
+        with torch.cuda.device(dev):
+            need = ctypes.c_size_t(0)
+            _lib.check(lib.drs_search_workspace_bytes(nq, nc, dim, kk, dt, ctypes.byref(need)))
+            ws = _workspace(dev, need.value)
+            scores = torch.empty(nq, kk, dtype=torch.float32, device=dev)
+            ids = torch.empty(nq, kk, dtype=torch.int64, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            epoch, ps, pi, pf = peer.pointer_arrays()
+            ev0 = ev1 = None
+            if profile is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+            _lib.check(lib.drs_search_sharded_p2p(q.data_ptr(), nq, loc.embeddings.data_ptr(), nc, dim, dt, kk, loc.id_base,
+                                                  self.rank, self.world, ps, pi, pf, epoch, scores.data_ptr(),
+                                                  ids.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+            if profile is not None:
+                ev1.record()
+                profile.append((ev0, ev1))
+        return scores, ids
 
 
 def all_gather_topk(slot_s: torch.Tensor, slot_i: torch.Tensor, group=None):

@@ -26,19 +26,55 @@ for nq, nc, dim, k in [(300, 100003, 128, 10), (1000, 1000000, 768, 10), (64, 7,
     queries = torch.nn.functional.normalize(torch.randn(nq, dim, generator=g, device=dev), dim=1).bfloat16()
     queries[0] = corpus[min(3, nc - 1)]
     lo, hi = drs_b200.shard_bounds(nc, rank, world)
-    index = drs_b200.ShardedDenseIndex(corpus[lo:hi].clone(), nc, device=dev)
-    s, i = index.search(queries, k)
+    index = drs_b200.ShardedDenseIndex(corpus[lo:hi].clone(), nc, device=dev)                      # auto: fused p2p
+    index_nccl = drs_b200.ShardedDenseIndex(corpus[lo:hi].clone(), nc, device=dev, exchange="nccl")
     fs, fi = drs_b200.search(queries, corpus, k)
-    same = torch.equal(i, fi) and torch.equal(s, fs)
+    same = True
+    for rep in range(3):                                                                            # epochs / both buffer parities
+        s, i = index.search(queries, k)
+        same = same and torch.equal(i, fi) and torch.equal(s, fs)
+    s2, i2 = index_nccl.search(queries, k)
+    same = same and torch.equal(i2, fi) and torch.equal(s2, fs)
+    if nq > 64:                                                                                     # a smaller batch on the same buffers
+        s3, i3 = index.search(queries[:17], k)
+        same = same and torch.equal(i3, fi[:17]) and torch.equal(s3, fs[:17])
     rv, ri = dense_topk.search(queries[:32].cpu(), corpus.cpu(), k)
     oracle_ok = torch.equal(i[:32].cpu()[:, 0], ri[:, 0]) and torch.allclose(s[:32].cpu(), rv, rtol=2e-2, atol=1e-4)
     tie_ok = nc <= 100 or i[0, :2].tolist() == [3, nc - 1]
     flag = torch.tensor([int(same and oracle_ok and tie_ok)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"sharded x{world} nq={nq} nc={nc} dim={dim} k={k}: equal_to_single_gpu={same} oracle={oracle_ok} "
+        print(f"sharded x{world} [{index.exchange}] nq={nq} nc={nc} dim={dim} k={k}: equal_to_single_gpu={same} oracle={oracle_ok} "
               f"tie={tie_ok} all_ranks={bool(flag.item())}", flush=True)
     ok = ok and bool(flag.item())
+
+# latency of the exchange in the small-batch regime: fused p2p kernel vs select + 2 all-gathers + merge
+nc, dim, k = 4_000_000, 768, 10
+g = torch.Generator(device=dev).manual_seed(1337 + rank)
+lo, hi = drs_b200.shard_bounds(nc, rank, world)
+shard = torch.nn.functional.normalize(torch.randn(hi - lo, dim, generator=g, device=dev), dim=1).bfloat16()
+for nq in (16, 128, 10000):
+    q = torch.nn.functional.normalize(torch.randn(nq, dim, generator=torch.Generator(device=dev).manual_seed(5), device=dev), dim=1).bfloat16()
+    res = {}
+    for mode in ("p2p", "nccl"):
+        idx = drs_b200.ShardedDenseIndex(shard, nc, device=dev, exchange=mode)
+        for _ in range(3):
+            out = idx.search(q, k)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            out = idx.search(q, k)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 20], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[mode] = (t.item(), out)
+    eq = torch.equal(res["p2p"][1][0], res["nccl"][1][0]) and torch.equal(res["p2p"][1][1], res["nccl"][1][1])
+    ok = ok and eq
+    if rank == 0:
+        print(f"exchange latency x{world} nq={nq} rows/rank={hi - lo}: p2p {res['p2p'][0]:.3f} ms/search, nccl {res['nccl'][0]:.3f} ms/search, same={eq}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
