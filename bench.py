@@ -229,8 +229,6 @@ def run_b200(args):
     queries = torch.nn.functional.normalize(torch.randn(nq, dim, generator=gq, device=dev), dim=1).bfloat16()
     queries_host = queries.cpu().pin_memory()
     index = drs_b200.ShardedDenseIndex(shard, nc, device=dev) if world > 1 else drs_b200.DenseIndex(shard, device=dev)
-    # scan + select on one GPU; sharded: scan + the fused select/exchange/merge kernel (p2p), or scan + select + merge (nccl)
-    launches_per_step = 2 if (world == 1 or index.exchange == "p2p") else 3
 
     def barrier():
         if world > 1:
@@ -335,6 +333,8 @@ def run_b200(args):
                 "hbm_frac": ach_gbs / peaks["hbm_gbs"], "mma_frac": ach_tflops / peaks["tflops"],
                 "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": bytes_alg}
 
+    # scan + select on one GPU; sharded: scan + the fused select/exchange/merge kernel (p2p), or scan + select + merge (nccl)
+    launches_per_step = 2 if (world == 1 or index.exchange == "p2p") else 3
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "claims/s", "n_gpus": world, "steps": args.steps,
