@@ -26,7 +26,7 @@ extern "C" {
 
 enum { DRS_OK = 0, DRS_ERR_INVALID = 1, DRS_ERR_CUDA = 2, DRS_ERR_UNSUPPORTED = 3, DRS_ERR_WORKSPACE = 4 };
 enum { DRS_F32 = 0, DRS_BF16 = 1 };
-#define DRS_MAX_K 256  /* k > 32: adaptive passes over the corpus (at most ceil(k/32), usually one) */
+#define DRS_MAX_K 256  /* k > 16: adaptive passes over the corpus (at most ceil(k/16), usually one) */
 
 int drs_version(void);
 const char* drs_last_error(void);
@@ -53,11 +53,12 @@ int drs_get_option(const char* name, int* value);
  *   out_scores device [nq, k] fp32, descending;  out_ids device [nq, k] int64 = row + id_base
  *   ties are broken by the lower row index; when nc < k the tail is (-inf, -1).
  * DRS_BF16 needs dim % 8 == 0 and 16-byte aligned base pointers (TMA); k <= DRS_MAX_K.
- * The running top-k lists hold 32 entries per (claim, corpus split) in registers.  k > 32 stays exact:
- * the select emits picks only while no split's full list could hide a better row, and a claim that stops
- * early is continued by a rescan strictly below its last pick.  At most ceil(k/32) passes are enqueued;
- * a pass with no open claim returns at once on the device (one pass does all the work unless more than
- * 32 of a claim's top-k fall into one of the ~74+ splits).
+ * The running top-k lists hold 16 (or, for 17 <= k on corpora with few splits, 32) entries per (claim, corpus
+ * split) in registers.  k beyond the list capacity stays exact: the select emits picks only while no
+ * split's full list could hide a better row, and a claim that stops early is continued by a rescan strictly
+ * below its last pick.  At most ceil(k/capacity) passes are enqueued; a pass with no open claim returns at
+ * once on the device (one pass does all the work unless more than 16 of a claim's top-k fall into one of
+ * the ~74+ splits).
  */
 int drs_search_workspace_bytes(int64_t nq, int64_t nc, int dim, int k, int dtype, size_t* bytes);
 int drs_search(const void* queries, int64_t nq, const void* corpus, int64_t nc, int dim, int dtype, int k,
@@ -100,7 +101,7 @@ int drs_search_l2(const void* queries, int64_t nq, const void* corpus, int64_t n
  *   epoch: 1, 2, 3, ... -- the same on all ranks, one more per call on the same buffers.  The caller alternates
  *       between two sets of gather buffers by epoch parity (flags are shared): a rank may run one call ahead
  *       of a peer that is still merging the previous one.
- * All ranks must make the same sequence of calls (it is a collective).  k <= 32, world <= 8.
+ * All ranks must make the same sequence of calls (it is a collective).  k <= 16, world <= 8.
  */
 int drs_exchange_flag_bytes(int64_t max_nq, int world, size_t* bytes);
 int drs_search_sharded_p2p(const void* queries, int64_t nq, const void* corpus, int64_t nc_local, int dim, int dtype,

@@ -151,7 +151,7 @@ drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int 
 constexpr int kTcColGroups = drs::GemmCfg<1>::EPI_GROUPS;
 inline size_t align256s(size_t x) { return (x + 255) & ~size_t(255); }
 constexpr size_t kWsRoundBytes = 256;   // round-barrier counter, zeroed before every scan
-constexpr size_t kWsHeaderBytes = 512;  // + per-pass "claims still open" counters of the adaptive k > 32 search
+constexpr size_t kWsHeaderBytes = 512;  // + per-pass "claims still open" counters of the adaptive multi-pass search
 inline int num_slots(const drs::GemmShape& s) { return s.num_splits * s.col_groups; }
 
 struct SearchPlan {
@@ -179,8 +179,6 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
   if (int rc = get_device_info(&di)) return rc;
   p->dtype = dtype;
   p->k = k;
-  p->kcap = k <= 16 ? 16 : 32;
-  p->passes = (k + 31) / 32;   // k > 32: passes of 32, each continuing below the previous pass's last pick
   if (dtype == DRS_BF16) {
     if (di.cc_major != 10) return fail(DRS_ERR_UNSUPPORTED, "the bf16 path needs an sm_100 device (tcgen05/TMEM); this is sm_%d%d", di.cc_major, di.cc_minor);
     if (dim % 8 != 0) return fail(DRS_ERR_INVALID, "bf16 path: dim must be a multiple of 8 (TMA 16-byte row pitch), got %d", dim);
@@ -199,7 +197,18 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
   } else {
     return fail(DRS_ERR_INVALID, "unknown dtype %d", dtype);
   }
-  // k > 32: per claim a continuation bound (u64) and the count of picks already emitted (int)
+  // List capacity per (claim, slot) and the pass count.  k <= 16: lists of 16, one pass.  Larger k: adaptive
+  // passes (merge.cuh) -- each pass is certain of >= kcap picks, so at most ceil(k / kcap) are enqueued and,
+  // when a claim's neighbours are spread over the slots, the first one finishes.  Lists of 16 cost about
+  // half of what lists of 32 cost in the epilogue (registers, insert depth), so they are used whenever the
+  // expected share of a slot, k / slots, is small (<= 4: P(> 16 in one slot) ~ 1e-6 for spread neighbours;
+  // clustered neighbours only add passes, never errors).  17 <= k <= 32 with few slots: lists of 32, one pass.
+  {
+    const int slots = num_slots(p->shape);
+    p->kcap = (k <= 16 || k <= 4 * slots) ? 16 : 32;
+    p->passes = (k + p->kcap - 1) / p->kcap;
+  }
+  // passes > 1: per claim a continuation bound (u64) and the count of picks already emitted (int)
   p->bound_bytes = p->passes > 1 ? align256s(static_cast<size_t>(nq) * sizeof(uint64_t)) + align256s(static_cast<size_t>(nq) * sizeof(int)) : 0;
   p->cand_bytes = align256s(static_cast<size_t>(nq) * num_slots(p->shape) * p->kcap * sizeof(uint64_t));
   p->pad_bytes = 0;
@@ -215,7 +224,7 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
       p->pad_bytes = align256s(static_cast<size_t>(padded) * dim * 2);
     }
   }
-  p->seed_slots = p->passes;   // == ceil(k / 32) when k > 32, else 1
+  p->seed_slots = p->passes;   // == ceil(k / kcap)
   p->seed_bytes = align256s(static_cast<size_t>(nq) * p->seed_slots * sizeof(uint32_t));
   p->ws_bytes = kWsHeaderBytes + p->bound_bytes + p->cand_bytes + p->pad_bytes + p->seed_bytes;
   return DRS_OK;
@@ -326,20 +335,20 @@ int launch_select(const uint64_t* ws, int64_t nq, int nslots, int kcap, int k, i
 }
 
 template <int SL>
-int launch_merge_runs_sl(const uint64_t* ws, int64_t nq, int nslots, int k, int64_t id_base, float* out_scores,
+int launch_merge_runs_sl(const uint64_t* ws, int64_t nq, int nslots, int kcap, int k, int64_t id_base, float* out_scores,
                          int64_t* out_ids, uint64_t* bound, int* done, const unsigned int* active_in,
                          unsigned int* remaining_out, const float* row_term, cudaStream_t st) {
   const int blocks = static_cast<int>((nq + 3) / 4);
-  drs::merge_runs_kernel<SL, 32><<<blocks, 128, 0, st>>>(ws, (int)nq, nslots, k, id_base, out_scores,
+  drs::merge_runs_kernel<SL><<<blocks, 128, 0, st>>>(ws, (int)nq, nslots, kcap, k, id_base, out_scores,
                                                           reinterpret_cast<long long*>(out_ids), k, bound, done,
                                                           active_in, remaining_out, row_term);
   DRS_CUDA(cudaGetLastError());
   return DRS_OK;
 }
-int launch_merge_runs(const uint64_t* ws, int64_t nq, int nslots, int k, int64_t id_base, float* out_scores,
+int launch_merge_runs(const uint64_t* ws, int64_t nq, int nslots, int kcap, int k, int64_t id_base, float* out_scores,
                       int64_t* out_ids, uint64_t* bound, int* done, const unsigned int* active_in,
                       unsigned int* remaining_out, const float* row_term, cudaStream_t st) {
-#define DRS_RUNS(SL) return launch_merge_runs_sl<SL>(ws, nq, nslots, k, id_base, out_scores, out_ids, bound, done, active_in, remaining_out, row_term, st)
+#define DRS_RUNS(SL) return launch_merge_runs_sl<SL>(ws, nq, nslots, kcap, k, id_base, out_scores, out_ids, bound, done, active_in, remaining_out, row_term, st)
   if (nslots <= 32) DRS_RUNS(1);
   if (nslots <= 64) DRS_RUNS(2);
   if (nslots <= 96) DRS_RUNS(3);
@@ -451,7 +460,7 @@ int drs_search_scan(const void* queries, int64_t nq, const void* corpus, int64_t
                     void* workspace, size_t workspace_bytes, void* stream) {
   SearchPlan p;
   if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
-  if (p.passes > 1) return fail(DRS_ERR_UNSUPPORTED, "drs_search_scan/select serve k <= 32; use drs_search for k = %d", k);
+  if (p.passes > 1) return fail(DRS_ERR_UNSUPPORTED, "drs_search_scan/select serve single-pass searches (k <= 16, or <= 32 on small corpora); use drs_search for k = %d", k);
   if (int rc = check_search_args(p, queries, corpus, workspace, workspace_bytes)) return rc;
   return scan_pass(p, queries, corpus, dim, workspace, k, nullptr, static_cast<cudaStream_t>(stream));
 }
@@ -461,7 +470,7 @@ int drs_search_select(const void* workspace, int64_t nq, int64_t nc, int dim, in
   if (!workspace || !out_scores || !out_ids) return fail(DRS_ERR_INVALID, "null pointer argument");
   SearchPlan p;
   if (int rc = plan_search(nq, nc, dim, k, dtype, &p)) return rc;
-  if (p.passes > 1) return fail(DRS_ERR_UNSUPPORTED, "drs_search_scan/select serve k <= 32; use drs_search for k = %d", k);
+  if (p.passes > 1) return fail(DRS_ERR_UNSUPPORTED, "drs_search_scan/select serve single-pass searches (k <= 16, or <= 32 on small corpora); use drs_search for k = %d", k);
   return launch_select(reinterpret_cast<const uint64_t*>(static_cast<const char*>(workspace) + kWsHeaderBytes), nq,
                        num_slots(p.shape), p.kcap, k, id_base, out_scores, out_ids, nullptr, static_cast<cudaStream_t>(stream));
 }
@@ -488,8 +497,8 @@ int run_search(SearchPlan& p, const void* queries, const void* corpus, int dim, 
   DRS_CUDA(cudaMemsetAsync(done, 0, static_cast<size_t>(nq) * sizeof(int), st));
   for (int pass = 0; pass < p.passes; ++pass) {
     const unsigned int* active = pass ? open_claims + (pass - 1) : nullptr;
-    if (int rc = scan_pass(p, queries, corpus, dim, workspace, 32, pass ? bound : nullptr, st, col_bias, extra_bytes, active)) return rc;
-    if (int rc = launch_merge_runs(cand, nq, num_slots(p.shape), k, id_base, out_vals, out_ids, bound, done, active,
+    if (int rc = scan_pass(p, queries, corpus, dim, workspace, p.kcap, pass ? bound : nullptr, st, col_bias, extra_bytes, active)) return rc;
+    if (int rc = launch_merge_runs(cand, nq, num_slots(p.shape), p.kcap, k, id_base, out_vals, out_ids, bound, done, active,
                                    open_claims + pass, row_term, st)) return rc;
   }
   return DRS_OK;

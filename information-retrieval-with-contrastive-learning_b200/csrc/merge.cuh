@@ -125,13 +125,13 @@ select_runs_kernel(const uint64_t* __restrict__ ws, int nq, int nslots, int kcap
 // per pick, the winning lane advances its run.  A full run (KCAP entries) may hide more of its
 // slot below its last key; B = the largest such last key.  Every pick >= B is certainly the next
 // best of the whole corpus (anything hidden is < its run's last key <= B), so picks are emitted
-// while they stay >= B -- at least KCAP per pass, usually all k on the first.  A claim that stops
+// while they stay >= B -- at least kcap per pass, usually all k on the first.  A claim that stops
 // early leaves `bound` = its last pick and `done` = its count; the next pass rescans only keys
 // below the bound and continues.  `remaining[0]` counts the unfinished claims of this pass: the
 // next scan and merge return at once when it is zero.  Claims already complete are skipped.
-template <int SL, int KCAP>
+template <int SL>
 __global__ void __launch_bounds__(128)
-merge_runs_kernel(const uint64_t* __restrict__ ws, int nq, int nslots, int k, long long id_base,
+merge_runs_kernel(const uint64_t* __restrict__ ws, int nq, int nslots, int kcap, int k, long long id_base,
                   float* __restrict__ out_scores, long long* __restrict__ out_ids, int ld_out,
                   uint64_t* __restrict__ bound, int* __restrict__ done, const unsigned int* __restrict__ active_in,
                   unsigned int* __restrict__ remaining_out, const float* __restrict__ row_term) {
@@ -141,7 +141,7 @@ merge_runs_kernel(const uint64_t* __restrict__ ws, int nq, int nslots, int k, lo
   if (q >= nq) return;
   int r = done[q];
   if (r >= k) return;
-  const uint64_t* src = ws + static_cast<size_t>(q) * nslots * KCAP;
+  const uint64_t* src = ws + static_cast<size_t>(q) * nslots * kcap;
   uint64_t head[SL];
   int pos[SL];
   uint64_t hidden = 0ull;  // B
@@ -151,8 +151,8 @@ merge_runs_kernel(const uint64_t* __restrict__ ws, int nq, int nslots, int k, lo
     pos[i] = 0;
     head[i] = 0ull;
     if (slot < nslots) {
-      head[i] = src[static_cast<size_t>(slot) * KCAP];
-      const uint64_t last = src[static_cast<size_t>(slot) * KCAP + KCAP - 1];
+      head[i] = src[static_cast<size_t>(slot) * kcap];
+      const uint64_t last = src[static_cast<size_t>(slot) * kcap + kcap - 1];
       hidden = last > hidden ? last : hidden;
     }
   }
@@ -171,7 +171,7 @@ merge_runs_kernel(const uint64_t* __restrict__ ws, int nq, int nslots, int k, lo
       for (int i = 0; i < SL; ++i) {
         if (head[i] == best) {
           ++pos[i];
-          head[i] = pos[i] < KCAP ? src[static_cast<size_t>(lane + 32 * i) * KCAP + pos[i]] : 0ull;
+          head[i] = pos[i] < kcap ? src[static_cast<size_t>(lane + 32 * i) * kcap + pos[i]] : 0ull;
         }
       }
     }

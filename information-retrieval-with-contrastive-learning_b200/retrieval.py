@@ -88,7 +88,7 @@ def search(queries: torch.Tensor, corpus: torch.Tensor, k: int, *, id_base: int 
         scores = torch.empty(nq, kk, dtype=torch.float32, device=dev)
         ids = torch.empty(nq, kk, dtype=torch.int64, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        if profile is None or kk > 32:      # the scan/select split serves single-pass searches (k <= 32)
+        if profile is None or kk > 16:      # the scan/select split serves single-pass searches
             _lib.check(lib.drs_search(queries.data_ptr(), nq, corpus.data_ptr(), nc, dim, dt, kk, int(id_base),
                                       scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(), stream))
         else:
@@ -442,7 +442,7 @@ class ShardedDenseIndex:
 
     * ``exchange='p2p'``: ONE kernel per search selects the shard's top-k, stores it into every peer's
       buffer over NVLink peer memory, waits on per-claim-block flags and merges (csrc/exchange.cuh);
-      needs the NCCL backend's symmetric memory, k <= 32, <= 8 ranks, no empty shard;
+      needs the NCCL backend's symmetric memory, k <= 16, <= 8 ranks, no empty shard;
     * ``exchange='nccl'``: select, ``all_gather_into_tensor`` of scores and ids, merge kernel (any backend).
 
     ``exchange='auto'`` (default) takes 'p2p' when its conditions hold, else 'nccl'.
@@ -495,7 +495,7 @@ class ShardedDenseIndex:
     def search(self, queries: torch.Tensor, k: int = 1, profile: Optional[list] = None):
         kk = min(int(k), self.total_rows)
         nq = queries.shape[0]
-        if self.exchange == "p2p" and 0 < kk <= 32 and 0 < nq <= _PeerExchange.MAX_NQ:
+        if self.exchange == "p2p" and 0 < kk <= 16 and 0 < nq <= _PeerExchange.MAX_NQ:
             if self._peer_exchange(nq * kk) is not None:
                 return self._search_p2p(queries, kk, profile)
         s, i = (self.local.search(queries, min(kk, max(self.local.num_docs, 1)), profile=profile)
