@@ -165,7 +165,9 @@ struct SearchPlan {
   size_t bound_bytes;
   size_t cand_bytes;
   size_t seed_bytes;  // threshold seeds [nq][seed_slots] (epilogues.cuh), zeroed before every scan
-  int seed_slots;     // ceil(k / kcap): that many disjoint ranges with >= kcap rows above a score bound k rows
+  int seed_slots;     // certificates kept per claim: ceil(k / seed_group)
+  int seed_group;     // rows certified by one published value (epilogues.cuh)
+  int seed_chunks;    // values a unit publishes: seed_chunks * seed_group <= entries selected per pass
   size_t pad_bytes;   // bf16: zero-padded copy of the claims when nq is not a multiple of the A tile (see scan_pass)
   int64_t a_rows;     // rows of the A operand as the tensor map sees it (nq rounded up when padded)
   size_t ws_bytes;
@@ -224,7 +226,12 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
       p->pad_bytes = align256s(static_cast<size_t>(padded) * dim * 2);
     }
   }
-  p->seed_slots = p->passes;   // == ceil(k / kcap)
+  {
+    const int k_pass = p->passes > 1 ? p->kcap : k;   // entries a unit's list is asked for
+    p->seed_chunks = std::min(5, k_pass);
+    p->seed_group = k_pass / p->seed_chunks;
+    p->seed_slots = (k + p->seed_group - 1) / p->seed_group;
+  }
   p->seed_bytes = align256s(static_cast<size_t>(nq) * p->seed_slots * sizeof(uint32_t));
   p->ws_bytes = kWsHeaderBytes + p->bound_bytes + p->cand_bytes + p->pad_bytes + p->seed_bytes;
   return DRS_OK;
@@ -277,11 +284,11 @@ int launch_search_tc(const SearchPlan& p, const void* queries, const void* corpu
                      const uint64_t* bound, const float* col_bias, uint32_t* seeds, cudaStream_t st) {
   if (col_bias != nullptr) {
     using Epi = drs::TopKEpilogue<KCAP, true>;
-    typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, col_bias, 2.0f, seeds, p.seed_slots};
+    typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, col_bias, 2.0f, seeds, p.seed_slots, p.seed_group, p.seed_chunks};
     return launch_gemm_tc<CG, Epi>(queries, corpus, dim, p.shape, p.grid, ep, st, p.a_rows);
   }
   using Epi = drs::TopKEpilogue<KCAP>;
-  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, nullptr, 1.0f, seeds, p.seed_slots};
+  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, nullptr, 1.0f, seeds, p.seed_slots, p.seed_group, p.seed_chunks};
   return launch_gemm_tc<CG, Epi>(queries, corpus, dim, p.shape, p.grid, ep, st, p.a_rows);
 }
 
@@ -290,12 +297,12 @@ int launch_search_f32(const SearchPlan& p, const void* queries, const void* corp
                       const uint64_t* bound, const float* col_bias, uint32_t* seeds, cudaStream_t st) {
   if (col_bias != nullptr) {
     using Epi = drs::TopKEpilogue<KCAP, true>;
-    typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, col_bias, 2.0f, seeds, p.seed_slots};
+    typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, col_bias, 2.0f, seeds, p.seed_slots, p.seed_group, p.seed_chunks};
     return launch_gemm_simt<Epi, false>(static_cast<const float*>(queries), dim, static_cast<const float*>(corpus),
                                         dim, dim, p.shape, p.grid, ep, st);
   }
   using Epi = drs::TopKEpilogue<KCAP>;
-  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, nullptr, 1.0f, seeds, p.seed_slots};
+  typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, nullptr, 1.0f, seeds, p.seed_slots, p.seed_group, p.seed_chunks};
   return launch_gemm_simt<Epi, false>(static_cast<const float*>(queries), dim, static_cast<const float*>(corpus), dim,
                                       dim, p.shape, p.grid, ep, st);
 }

@@ -25,14 +25,19 @@ struct TopKEpilogue {
     const float* col_bias;  // BIASED: ranked value = score_scale * dot + col_bias[col]
     float score_scale;      //   (squared-L2 search: 2 x.c - |c|^2, src/contrastor/utils.py:64-67)
     // Threshold seeding across units.  seeds: [rows_a][seed_slots] ordered-uint32 scores, zeroed before the
-    // scan.  A unit that ends with a full list publishes its k-th best; the seed_slots largest values published
-    // for a claim come from seed_slots DISJOINT corpus ranges, each holding >= k rows that score at least that
-    // much, so with seed_slots * k >= (the k the caller wants) the smallest of them is a lower bound on the
-    // final k-th best score: later units of the claim start from it instead of from -inf and stay on the
-    // fast path (a fresh list needs ~k ln(n/k) inserts to warm up, and one lane's insert stalls its warp).
-    // Any stale or missing seed is merely a weaker bound -- the result is exact either way.
+    // scan.  A unit's sorted list is cut into seed_chunks groups of seed_group entries; group c's smallest
+    // entry v_c = sc[c * seed_group - 1] certifies seed_group rows of the unit's corpus range that score
+    // >= v_c, disjoint from every other group of every unit.  Each claim keeps the seed_slots largest
+    // certificates published so far (replace-the-minimum by compare-and-swap); with seed_slots * seed_group >=
+    // (the k the caller wants) their minimum is a lower bound on the final k-th best score.  Later units of the
+    // claim start from it instead of from -inf and stay on the fast path (a fresh list needs ~k ln(n/k) inserts
+    // to warm up, and one lane's insert stalls its warp).  Every certified row is in a candidate list, so
+    // the select still sees >= k rows at or above the bound; stale or missing seeds only weaken it -- the
+    // result is exact either way.
     uint32_t* seeds;
     int seed_slots;
+    int seed_group;
+    int seed_chunks;
   };
   TopKList<KCAP> list;
   uint64_t bnd;
@@ -108,14 +113,25 @@ struct TopKEpilogue {
     uint64_t* dst = p.ws + (static_cast<size_t>(row) * p.num_slots + slot) * KCAP;
 #pragma unroll
     for (int j = 0; j < KCAP; ++j) dst[j] = list.key(j);
-    if (p.seeds != nullptr && list.kth > -INFINITY) {
-      // keep the seed_slots largest published values: each atomicMax leaves the larger in place and carries
-      // the smaller down, which conserves the multiset {slots, carry} under any interleaving
-      uint32_t v = float_to_ordered(list.kth);
+    if (p.seeds != nullptr) {
       uint32_t* a = p.seeds + static_cast<size_t>(row) * p.seed_slots;
-      for (int j = 0; j < p.seed_slots && v != 0u; ++j) {
-        const uint32_t old = atomicMax(a + j, v);
-        v = min(old, v);
+      for (int c = 1; c <= p.seed_chunks; ++c) {          // best group first: each success raises the minimum
+        const int pos = c * p.seed_group - 1;
+        float val = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < KCAP; ++j) val = (j == pos) ? list.sc[j] : val;
+        if (!(val > list.floor)) break;                   // empty, or below what the claim already had at the start
+        const uint32_t v = float_to_ordered(val);
+        for (;;) {
+          uint32_t mn = 0xFFFFFFFFu;
+          int mi = 0;
+          for (int j = 0; j < p.seed_slots; ++j) {
+            const uint32_t x = __ldcg(a + j);
+            if (x < mn) { mn = x; mi = j; }
+          }
+          if (v <= mn) break;                             // not among the seed_slots largest
+          if (atomicCAS(a + mi, mn, v) == mn) break;      // replaced the minimum; else someone else moved it: retry
+        }
       }
     }
   }

@@ -21,7 +21,7 @@
 // epoch parity: a rank can be at most one call ahead of its slowest peer (it cannot finish call n+1
 // before every peer has published call n+1, i.e. finished reading call n).
 // All CTAs are co-resident (grid <= resident capacity) and every block publishes before it waits,
-// so the spin cannot deadlock; a wait that exceeds a few seconds traps with a hang report.
+// so the spin cannot deadlock; a wait that exceeds ~1.5 minutes traps with a hang report.
 #pragma once
 #include "merge.cuh"
 #include "ptx.cuh"
@@ -30,6 +30,9 @@ namespace drs {
 
 constexpr int kMaxPeers = 8;
 enum : uint32_t { kTagExchangeWait = 6 };
+// A peer's kernel starts whenever ITS host thread gets to the launch, so the wait must tolerate host-side skew
+// between ranks (seconds), not just device latency; it still ends a genuinely stuck exchange (~1.5 min).
+static constexpr long long kExchangeTimeoutCycles = 180000000000LL;
 
 struct ExchangePeers {
   float* scores[kMaxPeers];     // rank p's gather buffer: [world][nq][k] fp32   (peer-mapped pointers)
@@ -101,7 +104,7 @@ select_exchange_merge_kernel(const uint64_t* __restrict__ ws, int nq, int nslots
         const uint32_t v = lane < world ? ld_acquire_sys_u32(fl + lane) : epoch;
         if (__all_sync(0xffffffffu, static_cast<int32_t>(v - epoch) >= 0)) break;
         __nanosleep(200);
-        if (clock64() - t0 > kMbarTimeoutCycles) mbar_hang(kTagExchangeWait, epoch, static_cast<uint32_t>(rb));
+        if (clock64() - t0 > kExchangeTimeoutCycles) mbar_hang(kTagExchangeWait, epoch, static_cast<uint32_t>(rb));
       }
     }
     __syncthreads();
