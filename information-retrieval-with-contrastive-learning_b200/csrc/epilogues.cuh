@@ -89,21 +89,20 @@ struct TopKEpilogue {
     const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
     // fast path: nothing in this chunk beats the current k-th best of any row of the warp
     if (!__any_sync(0xffffffffu, mx > list.thr)) return;
-    // Slow path (rare once the lists have warmed up).  Each lane marks its own candidates, the
-    // warp walks the UNION of marked columns, and the insert code exists once (a 32-way unrolled
-    // version thrashes the instruction cache).  Lanes without a candidate at column j insert -inf,
-    // which is a no-op.
+    // Slow path (rare once the lists have warmed up): each lane walks ITS OWN candidate columns; the warp
+    // iterates max-over-lanes times (lanes that are done idle), not once per column of the union.  The insert
+    // code exists once (a 32-way unrolled version thrashes the instruction cache); pick32 selects v[j] for a
+    // per-lane j without dynamic register indexing.
     uint32_t mine = 0u;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if ((j < valid) && (__uint_as_float(v[j]) > list.thr)) mine |= 1u << j;
-    uint32_t todo = __reduce_or_sync(0xffffffffu, mine);
 #pragma unroll 1
-    while (todo) {
-      const int j = __ffs(todo) - 1;
-      todo &= todo - 1u;
+    while (mine) {
+      const int j = __ffs(mine) - 1;
+      mine &= mine - 1u;
       const float s = __uint_as_float(pick32(v, j));
-      const bool hit = ((mine >> j) & 1u) && (s > list.thr) && (make_key(s, static_cast<uint32_t>(col0 + j)) < bnd);
+      const bool hit = (s > list.thr) && (make_key(s, static_cast<uint32_t>(col0 + j)) < bnd);
       list.insert(hit ? s : -INFINITY, static_cast<uint32_t>(col0 + j), p.k);
     }
   }
