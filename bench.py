@@ -165,6 +165,62 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bench_other_configs(torch, drs_b200, dev, peaks, shard, queries, rank, world):
+    """The other BASELINE.json configs on this rank's GPU, reusing the resident corpus rows (a bounded few
+    hundred ms): configs[0] on the fp32 exact path (and the CPU idiom on the same data, timed in full),
+    configs[1] (5.4M pages, top-10) and this GPU's share of configs[4] (65 536 claims x 5.4M/8 rows, top-100)."""
+    import time
+    out = {}
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    dim = shard.shape[1]
+    # configs[0]: 1k claims x 100k x 768 fp32, top-5 (the reference's CPU-runnable case)
+    c32 = shard[:100_000].float()
+    q32 = queries[:1000].float()
+    ms = timed(lambda: drs_b200.search(q32, c32, 5), 5)
+    rec = {"workload": "1000 claims x 100000 x 768 fp32, top-5 (exact FFMA path)", "ms_per_step": ms,
+           "claims_per_s": 1000 / (ms * 1e-3), "tflops_fp32": 2.0 * 1000 * 100_000 * dim / (ms * 1e-3) / 1e12}
+    if rank == 0:
+        from oracle import dense_topk
+        qc, cc = q32.cpu(), c32.cpu()
+        dense_topk.search_fast(qc[:64], cc, 5)
+        t0 = time.perf_counter()
+        dense_topk.search_fast(qc, cc, 5)
+        t = time.perf_counter() - t0
+        rec["cpu_reference_idiom"] = {"ms_per_step": t * 1e3, "claims_per_s": 1000 / t, "cores": torch.get_num_threads(),
+                                      "sample": "the whole config (fp32 torch.matmul + topk)"}
+    out["configs[0]"] = rec
+    # configs[1]: 10k claims x 5.4M pages, top-10 on one GPU (only when this rank holds that many rows)
+    if shard.shape[0] >= 5_400_000:
+        c = shard[:5_400_000]
+        ms = timed(lambda: drs_b200.search(queries, c, 10), 3)
+        fl = 2.0 * queries.shape[0] * c.shape[0] * dim
+        out["configs[1]"] = {"workload": f"{queries.shape[0]} claims x 5400000 x {dim} bf16, top-10, 1 GPU", "ms_per_step": ms,
+                             "claims_per_s": queries.shape[0] / (ms * 1e-3), "tflops": fl / (ms * 1e-3) / 1e12,
+                             "mma_frac": fl / (ms * 1e-3) / 1e12 / peaks["tflops"]}
+    # configs[4]: 65 536 claims x 5.4M docs top-100 on 8 GPUs -> one GPU's share is 675 000 rows
+    rows = min(shard.shape[0], 675_000)
+    g = torch.Generator(device=dev).manual_seed(77)
+    q65 = torch.nn.functional.normalize(torch.randn(65536, dim, generator=g, device=dev), dim=1).bfloat16()
+    c = shard[:rows]
+    ms = timed(lambda: drs_b200.search(q65, c, 100), 3)
+    fl = 2.0 * 65536 * rows * dim
+    out["configs[4]_per_gpu_share"] = {"workload": f"65536 claims x {rows} x {dim} bf16 (5.4M docs / 8 GPUs), top-100, scan + select on one GPU",
+                                       "ms_per_step": ms, "claims_per_s_per_gpu_share": 65536 / (ms * 1e-3),
+                                       "tflops": fl / (ms * 1e-3) / 1e12, "mma_frac": fl / (ms * 1e-3) / 1e12 / peaks["tflops"]}
+    return out
+
+
 def bench_infonce(torch, drs_b200, dev, peaks, n=4096, dim=768, temperature=0.05, reps=20):
     """BASELINE configs[3] (contrastor training step): NCELoss forward + backward on one GPU through the
     module a trainer calls (contrastive_module.py:86-87 -> train.py:147), CUDA events, inputs resident."""
@@ -316,9 +372,10 @@ def run_b200(args):
                             "roofline_frac": max(t_hbm, t_mma) / (kms * 1e-3)})
 
     # ---- BASELINE configs[3]: in-batch InfoNCE, batch 4096 x 768, fused logits + softmax-CE fwd/bwd
-    infonce_line = None
+    infonce_line = other_configs = None
     if not args.no_extras and rank == 0:
         infonce_line = bench_infonce(torch, drs_b200, dev, peaks)
+        other_configs = bench_other_configs(torch, drs_b200, dev, peaks, shard, queries, rank, world)
 
     # ---- roofline of the dominant kernel (the fused score GEMM + top-k scan), per launch = per rank shard
     rows = hi - lo
@@ -356,8 +413,12 @@ def run_b200(args):
         }
         if regimes:
             line["small_batch_regime"] = regimes
+            line["small_batch_regime_note"] = (f"hbm_frac = algorithmic bytes / scan time / {peaks['hbm_gbs']:.0f} GB/s, the measured "
+                                               "copy bandwidth (read + write); a read-only stream can exceed it, so hbm_frac > 1 is possible")
         if infonce_line:
             line["infonce_config"] = infonce_line
+        if other_configs:
+            line["other_baseline_configs"] = other_configs
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_reference_rate(nq, nc, dim, k, args.cpu_seconds)
         print(json.dumps(line), flush=True)
