@@ -382,3 +382,21 @@ def test_threshold_seeding_keeps_ties_and_matches_unseeded(dtype, k):
     assert i1[0, :10].cpu().tolist() == list(range(100, 110))
     tol = (1e-5, 2e-6) if dtype == torch.float32 else (2e-2, 1e-4)
     _check(q, c, k, s1, i1, score_rtol=tol[0], gap=tol[1])
+
+
+def test_randomised_shape_sweep_against_the_oracle():
+    """Seeded sweep over awkward shapes (tiny and ragged claims / corpus / dim, k from 1 to 256, both dtypes):
+    ids wherever the gap allows, scores within tolerance, descending order, -1 padding when k > Nc."""
+    rng = np.random.RandomState(1337)
+    dims = [8, 16, 24, 72, 128, 200, 768]
+    for case in range(24):
+        dtype = torch.bfloat16 if case % 3 else torch.float32
+        nq = int(rng.choice([1, 2, 3, 17, 127, 129, 257, 700]))
+        nc = int(rng.choice([1, 5, 33, 255, 257, 1000, 4097, 30011]))
+        dim = int(rng.choice(dims)) if dtype == torch.bfloat16 else int(rng.choice(dims + [7, 50]))
+        k = int(rng.choice([1, 2, 5, 10, 16, 17, 32, 33, 100, 256]))
+        q, c = _data(nq, nc, dim, dtype, planted=bool(case % 2), seed=1000 + case)
+        s, i = drs_b200.search(q, c, k)
+        assert s.shape == (nq, min(k, nc)), (case, nq, nc, dim, k)
+        tol = (1e-5, 2e-6) if dtype == torch.float32 else (2e-2, 1e-4)
+        _check(q, c, k, s, i, score_rtol=tol[0], gap=tol[1])
