@@ -174,6 +174,12 @@ int drs_infonce_forward(const float* q, const float* k, const float* queue, int6
 int drs_infonce_backward(const float* q, const float* k, const float* queue, int64_t n, int dim, int64_t queue_len,
                          float inv_temperature, int precision, const float* lse, const float* grad_loss, float* dq,
                          float* dk, void* workspace, size_t workspace_bytes, void* stream);
+/* Same, for a caller that kept the forward's workspace untouched (same q, k, queue, shapes, precision): the packed
+ * operands and the row LSEs the forward left there are reused instead of being staged again. */
+int drs_infonce_backward_staged(const float* q, const float* k, const float* queue, int64_t n, int dim,
+                                int64_t queue_len, float inv_temperature, int precision, const float* lse,
+                                const float* grad_loss, float* dq, float* dk, void* workspace, size_t workspace_bytes,
+                                void* stream);
 
 /*
  * MoCo-form InfoNCE.  Replaces: InfoNCE.forward (src/contrastor/contrastive_loss.py:26-44):

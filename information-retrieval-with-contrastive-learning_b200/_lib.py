@@ -44,6 +44,8 @@ _SIGNATURES = {
     "drs_infonce_forward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_f32, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "drs_infonce_backward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_f32, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                                      c_sz, c_vp]),
+    "drs_infonce_backward_staged": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_f32, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                            c_sz, c_vp]),
     "drs_moco_workspace_bytes": (c_int, [c_i64, c_int, c_i64, c_int, ctypes.POINTER(c_sz)]),
     "drs_moco_forward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_f32, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "drs_moco_backward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_f32, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,

@@ -69,7 +69,10 @@ class _InfoNceFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             need = ctypes.c_size_t(0)
             _lib.check(lib.drs_infonce_workspace_bytes(n, dim, klen, prec, ctypes.byref(need)))
-            ws = _workspace(dev, need.value)
+            # when a backward will follow, the step owns its workspace: the packed operands and row LSEs the
+            # forward leaves there are reused by the backward instead of being staged a second time
+            keep = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+            ws = torch.empty(need.value, dtype=torch.uint8, device=dev) if keep else _workspace(dev, need.value)
             loss = torch.empty(1, dtype=torch.float32, device=dev)
             lse = torch.empty(2 * n, dtype=torch.float32, device=dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -77,6 +80,7 @@ class _InfoNceFunction(torch.autograd.Function):
                                                n, dim, klen, float(inv_t), prec, loss.data_ptr(), lse.data_ptr(),
                                                ws.data_ptr(), ws.numel(), stream))
         ctx.save_for_backward(qf, kf, qu if qu is not None else torch.empty(0, device=dev), lse)
+        ctx.staged_ws = ws if keep else None
         ctx.has_queue = qu is not None
         ctx.inv_t = float(inv_t)
         ctx.prec = prec
@@ -93,12 +97,15 @@ class _InfoNceFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             need = ctypes.c_size_t(0)
             _lib.check(lib.drs_infonce_workspace_bytes(n, dim, klen, ctx.prec, ctypes.byref(need)))
-            ws = _workspace(dev, need.value)
+            staged = ctx.staged_ws is not None and ctx.staged_ws.numel() >= need.value
+            ws = ctx.staged_ws if staged else _workspace(dev, need.value)
+            ctx.staged_ws = None            # a second backward through the same graph stages again (H overwrote nothing it needs, but keep it simple)
             g = grad_out.detach().reshape(1).to(device=dev, dtype=torch.float32).contiguous()
             dq = torch.empty_like(qf)
             dk = torch.empty_like(kf)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(lib.drs_infonce_backward(qf.data_ptr(), kf.data_ptr(), qu.data_ptr() if ctx.has_queue else None,
+            backward = lib.drs_infonce_backward_staged if staged else lib.drs_infonce_backward
+            _lib.check(backward(qf.data_ptr(), kf.data_ptr(), qu.data_ptr() if ctx.has_queue else None,
                                                 n, dim, klen, ctx.inv_t, ctx.prec, lse.data_ptr(), g.data_ptr(),
                                                 dq.data_ptr(), dk.data_ptr(), ws.data_ptr(), ws.numel(), stream))
         return dq.to(ctx.in_dtypes[0]), dk.to(ctx.in_dtypes[1]), None, None, None
