@@ -124,11 +124,17 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int dim, int 
 }
 
 // ------------------------------------------------------------------ work decomposition
-// units = num_m_tiles * splits, dealt round-robin to `groups` persistent clusters.  Pick the
-// smallest split count that makes the units a multiple of the groups (every cluster gets the same
-// number of equally long units), capped by the number of B tiles.
+// units = num_m_tiles * splits, dealt round-robin to `groups` persistent clusters; a unit is `tiles_per_split`
+// consecutive B tiles against one A tile.
+//   search (long_units = false): the smallest split count that makes the units a multiple of the groups
+//     (every cluster gets the same number of equally long units), capped by the number of B tiles; many
+//     medium units also feed the threshold seeding.
+//   square GEMMs of the losses (long_units = true): the makespan rounds * tiles_per_split is minimised and
+//     ties go to the LONGER unit.  A cluster that changes its A tile fetches it across the die-to-die link
+//     instead of from the near L2: on 8192^2 x 768 one-tile units ran the mainloop in 111 us, two-tile units
+//     (same makespan, half the unit starts) in 78 us -- cuBLAS takes 83 us for that GEMM.
 drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int rows_per_m_tile, int rows_per_b_tile,
-                          int groups, int forced_splits, int col_groups) {
+                          int groups, int forced_splits, int col_groups, bool long_units = false) {
   drs::GemmShape s;
   s.rows_a = static_cast<int>(rows_a);
   s.rows_b = static_cast<int>(rows_b);
@@ -136,6 +142,16 @@ drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int 
   s.num_m_tiles = static_cast<int>((rows_a + rows_per_m_tile - 1) / rows_per_m_tile);
   s.total_b_tiles = static_cast<int>((rows_b + rows_per_b_tile - 1) / rows_per_b_tile);
   int splits = forced_splits > 0 ? forced_splits : groups / std::gcd(s.num_m_tiles, groups);
+  if (forced_splits <= 0 && long_units) {
+    long long best = -1;
+    for (int cand = std::min(s.total_b_tiles, 4 * groups); cand >= 1; --cand) {  // descending: the last tie wins
+      const int tps = (s.total_b_tiles + cand - 1) / cand;
+      const int real = (s.total_b_tiles + tps - 1) / tps;
+      const long long units = static_cast<long long>(s.num_m_tiles) * real;
+      const long long makespan = (units + groups - 1) / groups * tps;
+      if (best < 0 || makespan <= best) { best = makespan; splits = cand; }
+    }
+  }
   splits = std::max(1, std::min(splits, s.total_b_tiles));
   s.tiles_per_split = (s.total_b_tiles + splits - 1) / splits;
   s.num_splits = (s.total_b_tiles + s.tiles_per_split - 1) / s.tiles_per_split;  // no empty split

@@ -27,11 +27,19 @@ def main():
     for n in (8192, 16384):
         f = torch.nn.functional.normalize(torch.randn(n, 768, generator=g, device=dev), dim=1).bfloat16()
         fl = 2.0 * n * n * 768
-        for flags, label in ((0, "full"), (1, "no_functor"), (3, "no_tmem_ld"), (7, "tma_only")):
-            drs.set_option("debug.flags", flags)
-            ms = scan_ms(f, f, 10)
-            print(f"{n}x{n}x768 {label:12s} {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s", flush=True)
+        for splits in (0, 16, 8):
+            drs.set_option("search.splits", splits)
+            for flags, label in ((0, "full"), (1, "no_functor"), (7, "tma_only")):
+                drs.set_option("debug.flags", flags)
+                ms = scan_ms(f, f, 10)
+                print(f"{n}x{n}x768 splits={splits:2d} {label:12s} {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s", flush=True)
         drs.set_option("debug.flags", 0)
+        drs.set_option("search.splits", 0)
+        for rb in (1, 0):
+            drs.set_option("tune.round_barrier", rb)
+            ms = scan_ms(f, f, 10)
+            print(f"{n}x{n}x768 round_barrier={rb} full {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s", flush=True)
+        drs.set_option("tune.round_barrier", 1)
         out = torch.empty(n, n, dtype=torch.bfloat16, device=dev)
         torch.matmul(f, f.T, out=out)
         torch.cuda.synchronize()
