@@ -10,7 +10,7 @@
  *     allocates nothing and keeps no state between calls except the options set below;
  *   - matrices are row-major and contiguous; `stream` is a cudaStream_t passed as void*
  *     (NULL = the legacy default stream); calls are asynchronous on that stream;
- *   - workspace: ask `*_workspace_bytes`, pass a device buffer at least that large;
+ *   - workspace: ask `*_workspace_bytes`, pass a 256-byte aligned device buffer at least that large;
  *   - return value: DRS_OK (0) or an error code; `drs_last_error()` has the message
  *     (thread local).  Nothing is thrown across the boundary.
  */

@@ -438,28 +438,34 @@ int scan_pass(SearchPlan& p, const void* queries, const void* corpus, int dim, v
               const uint64_t* bound, cudaStream_t st, const float* col_bias = nullptr, size_t extra_bytes = 0,
               const unsigned int* active = nullptr) {
   p.shape.active = active;
+  char* base = static_cast<char*>(workspace);
   uint32_t* seeds = nullptr;
-  if (g_opt.seed_thresholds && p.shape.num_splits > 1) {
-    seeds = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + kWsHeaderBytes + p.bound_bytes + extra_bytes +
-                                        p.cand_bytes + p.pad_bytes);
-    DRS_CUDA(cudaMemsetAsync(seeds, 0, p.seed_bytes, st));
-  }
-  uint64_t* ws = reinterpret_cast<uint64_t*>(static_cast<char*>(workspace) + kWsHeaderBytes + p.bound_bytes + extra_bytes);
+  if (g_opt.seed_thresholds && p.shape.num_splits > 1)
+    seeds = reinterpret_cast<uint32_t*>(base + kWsHeaderBytes + p.bound_bytes + extra_bytes + p.cand_bytes + p.pad_bytes);
+  uint64_t* ws = reinterpret_cast<uint64_t*>(base + kWsHeaderBytes + p.bound_bytes + extra_bytes);
+  p.shape.round_counter = nullptr;
+  char* pad = nullptr;
   if (p.dtype == DRS_BF16) {
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
-    if (p.pad_bytes) {  // zero-padded staging copy of the claims (plan_search explains why)
-      char* pad = reinterpret_cast<char*>(ws) + p.cand_bytes;
-      const size_t live = static_cast<size_t>(p.shape.rows_a) * dim * 2;
-      DRS_CUDA(cudaMemcpyAsync(pad, queries, live, cudaMemcpyDeviceToDevice, st));
-      DRS_CUDA(cudaMemsetAsync(pad + live, 0, static_cast<size_t>(p.a_rows) * dim * 2 - live, st));
-      queries = pad;
-    }
-    p.shape.round_counter = nullptr;
-    if (g_opt.round_barrier && p.grid <= di.num_sms) {   // all CTAs co-resident: the barrier cannot deadlock
-      DRS_CUDA(cudaMemsetAsync(workspace, 0, kWsRoundBytes, st));
+    if (g_opt.round_barrier && p.grid <= di.num_sms)   // all CTAs co-resident: the barrier cannot deadlock
       p.shape.round_counter = static_cast<unsigned int*>(workspace);
-    }
+    if (p.pad_bytes) pad = reinterpret_cast<char*>(ws) + p.cand_bytes;  // zero-padded claims (plan_search explains why)
+  }
+  // one staging launch: round counter, seeds, padded claims (merge.cuh::scan_prep_kernel)
+  if (p.shape.round_counter != nullptr || seeds != nullptr || pad != nullptr) {
+    const size_t seed_vec = seeds ? p.seed_bytes / 16 : 0;
+    const size_t live = pad ? static_cast<size_t>(p.shape.rows_a) * dim * 2 : 0;   // dim % 8 == 0: a multiple of 16
+    const size_t pad_vec = pad ? static_cast<size_t>(p.a_rows) * dim * 2 / 16 : 0;
+    const size_t work = std::max<size_t>(std::max(seed_vec, pad_vec), 16);
+    const int blocks = static_cast<int>(std::min<size_t>((work + 255) / 256, 2048));
+    drs::scan_prep_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<uint4*>(p.shape.round_counter), reinterpret_cast<uint4*>(seeds),
+                                                  seed_vec, static_cast<const uint4*>(queries), reinterpret_cast<uint4*>(pad),
+                                                  live / 16, pad_vec);
+    DRS_CUDA(cudaGetLastError());
+    if (pad) queries = pad;
+  }
+  if (p.dtype == DRS_BF16) {
     if (p.cg == 1) return p.kcap == 16 ? launch_search_tc<1, 16>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, seeds, st)
                                        : launch_search_tc<1, 32>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, seeds, st);
     return p.kcap == 16 ? launch_search_tc<2, 16>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, seeds, st)
@@ -473,6 +479,7 @@ int check_search_args(const SearchPlan& p, const void* queries, const void* corp
   if (!queries || !corpus) return fail(DRS_ERR_INVALID, "null pointer argument");
   if (!workspace || workspace_bytes < p.ws_bytes)
     return fail(DRS_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", p.ws_bytes, workspace_bytes);
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(DRS_ERR_INVALID, "workspace must be 256-byte aligned");
   if (p.dtype == DRS_BF16 && ((reinterpret_cast<uintptr_t>(queries) & 15) || (reinterpret_cast<uintptr_t>(corpus) & 15)))
     return fail(DRS_ERR_INVALID, "bf16 path: queries and corpus must be 16-byte aligned");
   return DRS_OK;

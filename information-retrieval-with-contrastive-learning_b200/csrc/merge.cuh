@@ -246,6 +246,21 @@ merge_pairs_kernel(const float* __restrict__ in_scores, const long long* __restr
   }
 }
 
+// Everything a scan needs staged, in ONE launch instead of four stream operations (each costs a few
+// microseconds of launch latency, which is what a small-batch search over a shard is made of): zero the
+// round-barrier counter and the threshold seeds, and build the zero-padded copy of the claims.
+// All regions are 16-byte aligned and a multiple of 16 bytes long (256-byte aligned workspace carve-up).
+__global__ void __launch_bounds__(256)
+scan_prep_kernel(uint4* __restrict__ round_counter, uint4* __restrict__ seeds, size_t seed_vec,
+                 const uint4* __restrict__ claims, uint4* __restrict__ pad, size_t live_vec, size_t pad_vec) {
+  const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  if (round_counter != nullptr && tid < 16) round_counter[tid] = zero;  // 256 bytes
+  for (size_t i = tid; i < seed_vec; i += stride) seeds[i] = zero;
+  for (size_t i = tid; i < pad_vec; i += stride) pad[i] = i < live_vec ? claims[i] : zero;
+}
+
 // |row|^2 in fp32 for fp32 or bf16 rows; out[r] = sign * |row|^2.  One warp per row.
 template <typename T>
 __global__ void row_sqnorm_kernel(const T* __restrict__ x, long long rows, int dim, float sign, float* __restrict__ out) {
