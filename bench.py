@@ -119,6 +119,11 @@ def cpu_reference_rate(nq, nc, dim, k, target_seconds, steps=1, warmup=0):
     claims/sec for the FULL corpus is extrapolated linearly in the row count."""
     import torch
     from oracle import dense_topk
+    # all host cores: torchrun exports OMP_NUM_THREADS=1 for its workers, which would make this a 1-thread baseline
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     threads = torch.get_num_threads()
     g = torch.Generator().manual_seed(1337)
     # calibrate on a small probe, then size the sample for ~target_seconds per step
