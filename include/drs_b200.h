@@ -40,6 +40,9 @@ int drs_set_option(const char* name, int value);
  * so a broken pipeline surfaces as a CUDA error instead of a hang).  flag == 0: none. */
 int drs_debug_hang_report(unsigned int out[6]);
 int drs_get_option(const char* name, int* value);
+/* Debug: how many clusters of `cluster_size` CTAs of the scan kernel (one CTA per SM, ~198 KB of shared memory)
+ * the current device can hold at once (cudaOccupancyMaxActiveClusters). */
+int drs_debug_max_clusters(int cluster_size, int* out);
 
 /*
  * Dense claim x corpus scoring with fused top-k select.

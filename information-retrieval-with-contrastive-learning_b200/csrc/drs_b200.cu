@@ -401,6 +401,28 @@ int drs_debug_hang_report(unsigned int out[6]) {
   return DRS_OK;
 }
 
+int drs_debug_max_clusters(int cluster_size, int* out) {
+  if (!out || cluster_size < 1 || cluster_size > 16) return fail(DRS_ERR_INVALID, "bad argument");
+  using Cfg = drs::GemmCfg<2>;
+  auto kern = drs::gemm_nt_tc_kernel<2, drs::TopKEpilogue<16>>;
+  DRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  if (cluster_size > 8) DRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(cluster_size * 64);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DRS_CUDA(cudaOccupancyMaxActiveClusters(out, kern, &cfg));
+  return DRS_OK;
+}
+
 int drs_set_option(const char* name, int value) {
   if (!name) return fail(DRS_ERR_INVALID, "null option name");
   if (!strcmp(name, "search.cta_group")) g_opt.cta_group = value;
