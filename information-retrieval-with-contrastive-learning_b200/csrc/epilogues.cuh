@@ -39,6 +39,7 @@ struct TopKEpilogue {
     int seed_group;
     int seed_chunks;
   };
+  static constexpr bool kUsesScratch = false;
   TopKList<KCAP> list;
   uint64_t bnd;
 

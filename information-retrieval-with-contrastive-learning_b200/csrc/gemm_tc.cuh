@@ -51,7 +51,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (CG == 1) ? 4 : 6;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int EPI_SCRATCH_PER_WARP = 2560;  // 32 rows x (64 + 16 pad) bytes: staging for coalesced epilogue stores
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 8 * EPI_SCRATCH_PER_WARP + 1024;  // + alignment slack
   static constexpr int EPI_GROUPS = 2;     // epilogue warps per TMEM lane quadrant
   static constexpr int EPI_THREADS = 128 * EPI_GROUPS;
   static constexpr int THREADS = 128 + EPI_THREADS;
@@ -64,6 +65,7 @@ enum : uint32_t { kTagProducerEmpty = 1, kTagMmaFull = 2, kTagMmaTmemEmpty = 3, 
 
 // Epi requirements:
 //   struct Params;                                        (trivially copyable, passed by value)
+//   static constexpr bool kUsesScratch;  if true: `uint8_t* scratch` member, EPI_SCRATCH_PER_WARP bytes of smem per warp
 //   __device__ void begin_unit(const Params&, int row, int m_tile, int split);
 //   __device__ void chunk(const Params&, int row, int col0, const uint32_t (&v)[32]);   fp32 bit patterns
 //   __device__ void end_unit(const Params&, int row, int m_tile, int slot);     slot = split * col_groups + group
@@ -208,6 +210,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int group = (warp - 4) >> 2; // which column group of every tile this warp owns
     const int row_in_tile = quad * 32 + lane;
     Epi epi;
+    if constexpr (Epi::kUsesScratch)  // a private staging area per epilogue warp, behind the barriers
+      epi.scratch = smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + (warp - 4) * Cfg::EPI_SCRATCH_PER_WARP;
     uint32_t it = 0;
     for (int u = cluster; u < num_units; u += nclusters) {
       const int m = u % shp.num_m_tiles, s = u / shp.num_m_tiles;
