@@ -260,14 +260,14 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
 }
 
 // ------------------------------------------------------------------ generic GEMM launchers
-template <int CG, class Epi>
+template <int CG, class Epi, int BN = 256>
 int launch_gemm_tc(const void* a, const void* b, int kdim, const drs::GemmShape& shp, int grid,
                    const typename Epi::Params& ep, cudaStream_t st, int64_t a_rows_alloc = 0) {
-  using Cfg = drs::GemmCfg<CG>;
+  using Cfg = drs::GemmCfg<CG, BN>;
   CUtensorMap ta, tb;
   if (int rc = make_tmap_bf16(&ta, a, a_rows_alloc > 0 ? a_rows_alloc : shp.rows_a, kdim, Cfg::BM)) return rc;
   if (int rc = make_tmap_bf16(&tb, b, shp.rows_b, kdim, Cfg::BN_CTA)) return rc;
-  auto kern = drs::gemm_nt_tc_kernel<CG, Epi>;
+  auto kern = drs::gemm_nt_tc_kernel<CG, Epi, BN>;
   DRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -40,16 +40,18 @@ struct GemmShape {
   const unsigned int* active;   // optional: the whole launch is a no-op when *active == 0 (adaptive k > 32 passes)
 };
 
-template <int CG>
+// BN_ = 256 is the only width instantiated: 128-wide tiles were tried for the GEMM with few B tiles (dF = H F) and
+// lost (139 vs 103 us) -- the A operand is then read from shared memory twice as often per flop.
+template <int CG, int BN_ = 256>
 struct GemmCfg {
   static constexpr int BM = 128;          // A rows per CTA (= TMEM lanes)
-  static constexpr int BN = 256;          // B rows per tile (= TMEM columns per accumulator stage)
+  static constexpr int BN = BN_;          // B rows per tile (= TMEM columns per accumulator stage)
   static constexpr int BN_CTA = BN / CG;  // B rows staged by one CTA
   static constexpr int BK = 64;           // K slice: 64 bf16 = one 128-byte swizzle row
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN_CTA * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (CG == 1) ? 4 : 6;
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;  // 256-wide: 4 (CG 1) / 6 (CG 2); 128-wide: 6 / 8
   static constexpr int BAR_BYTES = 256;
   static constexpr int EPI_SCRATCH_PER_WARP = 2560;  // 32 rows x (64 + 16 pad) bytes: staging for coalesced epilogue stores
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 8 * EPI_SCRATCH_PER_WARP + 1024;  // + alignment slack
@@ -69,11 +71,11 @@ enum : uint32_t { kTagProducerEmpty = 1, kTagMmaFull = 2, kTagMmaTmemEmpty = 3, 
 //   __device__ void begin_unit(const Params&, int row, int m_tile, int split);
 //   __device__ void chunk(const Params&, int row, int col0, const uint32_t (&v)[32]);   fp32 bit patterns
 //   __device__ void end_unit(const Params&, int row, int m_tile, int slot);     slot = split * col_groups + group
-template <int CG, class Epi>
-__global__ void __launch_bounds__(GemmCfg<CG>::THREADS, 1)
+template <int CG, class Epi, int BN = 256>
+__global__ void __launch_bounds__(GemmCfg<CG, BN>::THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmShape shp, const typename Epi::Params ep) {
-  using Cfg = GemmCfg<CG>;
+  using Cfg = GemmCfg<CG, BN>;
   if (shp.active != nullptr && *shp.active == 0u) return;  // uniform over the grid: nothing left to rescan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
