@@ -49,8 +49,16 @@ struct TopKEpilogue {
     if (bnd == 0ull) {
       floor = INFINITY;  // this claim is complete: nothing is eligible, stay on the fast path
     } else if (p.seeds != nullptr && row < p.rows_a) {
+      // four independent L2 loads in flight per step (a serial chain of up to 86 L2 round trips at every unit
+      // start showed up in the ncu samples)
+      const uint32_t* a = p.seeds + static_cast<size_t>(row) * p.seed_slots;
       uint32_t lo = 0xFFFFFFFFu;
-      for (int j = 0; j < p.seed_slots; ++j) lo = min(lo, __ldcg(p.seeds + static_cast<size_t>(row) * p.seed_slots + j));
+      int j = 0;
+      for (; j + 3 < p.seed_slots; j += 4) {
+        const uint32_t x0 = __ldcg(a + j), x1 = __ldcg(a + j + 1), x2 = __ldcg(a + j + 2), x3 = __ldcg(a + j + 3);
+        lo = min(lo, min(min(x0, x1), min(x2, x3)));
+      }
+      for (; j < p.seed_slots; ++j) lo = min(lo, __ldcg(a + j));
       // strictly below the bound, so that rows TYING it (with a lower index) still enter
       if (lo != 0u) floor = ordered_to_float(lo - 1u);
     }

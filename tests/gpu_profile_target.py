@@ -27,6 +27,9 @@ def main():
         r1 = min(nc, r0 + (1 << 20))
         c[r0:r1] = torch.nn.functional.normalize(torch.randn(r1 - r0, 768, generator=g, device=dev), dim=1)
     q = torch.nn.functional.normalize(torch.randn(nq, 768, generator=g, device=dev), dim=1).bfloat16()
+    for name in os.environ.get("DRS_OPTIONS", "").split(","):          # e.g. DRS_OPTIONS=tune.round_barrier=0
+        if "=" in name:
+            drs.set_option(name.split("=")[0], int(name.split("=")[1]))
     for _ in range(3):
         s, i = drs.search(q, c, k)
     torch.cuda.synchronize()
