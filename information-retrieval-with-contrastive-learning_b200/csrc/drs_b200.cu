@@ -200,11 +200,13 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
   if (dtype == DRS_BF16) {
     if (di.cc_major != 10) return fail(DRS_ERR_UNSUPPORTED, "the bf16 path needs an sm_100 device (tcgen05/TMEM); this is sm_%d%d", di.cc_major, di.cc_minor);
     if (dim % 8 != 0) return fail(DRS_ERR_INVALID, "bf16 path: dim must be a multiple of 8 (TMA 16-byte row pitch), got %d", dim);
-    // CTA pair (256-row A tiles) for large batches; single CTAs (128-row tiles) up to 512 claims (measured over 8M
-    // rows: 192 / 256 / 384 / 512 claims 2.99 / 3.20 / 4.41 / 5.49 ms against 3.32 / 3.25 / 5.68 / 6.35 ms for pairs;
-    // at 1024 the pair wins, 10.3 vs 11.4 ms) and up to 1024 when they pad the batch less
+    // CTA pair (256-row A tiles) for large batches; single CTAs (128-row tiles) up to 128 claims, and near the
+    // ridge of the two roofs (<= 1024 claims) whenever they pad the batch less: 384 claims are 3 x 128 exactly
+    // but 2 x 256 with a quarter of every MMA wasted (15.3 vs 16.9 ms over 25M rows, 3.5 vs 4.4 ms over 6.25M).
+    // With equal padding (192, 256, 512 claims) the pair is the better choice on the big corpus (less L2 -> SM
+    // traffic per flop): 9.1 / 9.6 / 18.1 ms against 10.2 / 11.9 / 20.9 ms over 25M rows.
     int cg = 2;
-    if (nq <= 512) cg = 1;
+    if (nq <= 128) cg = 1;
     else if (nq <= 1024 && (nq + 127) / 128 * 128 < (nq + 255) / 256 * 256) cg = 1;
     if (g_opt.cta_group) cg = g_opt.cta_group;
     if (cg != 1 && cg != 2) return fail(DRS_ERR_INVALID, "search.cta_group must be 0, 1 or 2");
