@@ -21,6 +21,7 @@ What is executed, unmodified, from /root/reference:
 * sklearn's ``cosine_similarity`` + the loop at
   preprocessing/build_docs_sentence_similarity.py:52-65, restated verbatim in a local
   function because the module downloads nltk corpora at import time     -> pairs.npz
+* the commented dense diagnostic of src/evaluation.py:112, evaluated literally           -> paired.npz
 """
 import os
 import sys
@@ -171,9 +172,22 @@ def gen_pairs():
     np.savez_compressed(os.path.join(HERE, "pairs.npz"), **out)
 
 
+def gen_paired():
+    """The dense diagnostic the reference left commented out, src/evaluation.py:110-115, evaluated literally:
+    `(clm_vec * evdn_vec).sum(dim=-1).mean()` on L2-normalised vectors shaped like `ctx2vec` output
+    (contrastive_module.py:96-112: [B, 128], normalised)."""
+    g = torch.Generator().manual_seed(1337)
+    clm_vec = _unit(torch.randn(64, 128, generator=g))
+    evdn_vec = _unit(clm_vec + 0.5 * torch.randn(64, 128, generator=g))
+    per_pair = (clm_vec * evdn_vec).sum(dim=-1)                      # :112
+    np.savez_compressed(os.path.join(HERE, "paired.npz"), clm=clm_vec.numpy(), evdn=evdn_vec.numpy(),
+                        per_pair=per_pair.numpy(), mean=np.float32(per_pair.mean().item()))
+
+
 if __name__ == "__main__":
     torch.manual_seed(1337)
     gen_infonce()
     gen_closest_docs()
     gen_pairs()
+    gen_paired()
     print("golden vectors written to", HERE)

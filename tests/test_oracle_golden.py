@@ -130,3 +130,11 @@ def test_topk_tie_rule_and_chunking():
     assert i.shape == (17, 4)
     vf, jf = dense_topk.search_fast(q, c, 10)
     torch.testing.assert_close(vf, v_full, rtol=1e-6, atol=1e-6)
+
+
+def test_paired_scores_match_the_reference_expression(golden_dir):
+    """src/evaluation.py:112 evaluated literally by the generator -> oracle restatement."""
+    z = np.load(os.path.join(golden_dir, "paired.npz"))
+    got = dense_topk.paired_scores(torch.from_numpy(z["clm"]), torch.from_numpy(z["evdn"]))
+    np.testing.assert_allclose(got.numpy(), z["per_pair"], rtol=0, atol=1e-7)
+    assert abs(got.mean().item() - float(z["mean"])) < 1e-7

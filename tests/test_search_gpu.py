@@ -400,3 +400,13 @@ def test_randomised_shape_sweep_against_the_oracle():
         assert s.shape == (nq, min(k, nc)), (case, nq, nc, dim, k)
         tol = (1e-5, 2e-6) if dtype == torch.float32 else (2e-2, 1e-4)
         _check(q, c, k, s, i, score_rtol=tol[0], gap=tol[1])
+
+
+def test_paired_scores_golden(golden_dir):
+    """The reference's own expression (src/evaluation.py:112), run by tests/golden/make_golden.py."""
+    import os
+    z = np.load(os.path.join(golden_dir, "paired.npz"))
+    clm, evdn = torch.from_numpy(z["clm"]).to(DEV), torch.from_numpy(z["evdn"]).to(DEV)
+    out = drs_b200.paired_scores(clm, evdn)
+    np.testing.assert_allclose(out.cpu().numpy(), z["per_pair"], rtol=1e-5, atol=1e-6)
+    assert abs(out.mean().item() - float(z["mean"])) < 1e-6
