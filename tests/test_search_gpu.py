@@ -410,3 +410,24 @@ def test_paired_scores_golden(golden_dir):
     out = drs_b200.paired_scores(clm, evdn)
     np.testing.assert_allclose(out.cpu().numpy(), z["per_pair"], rtol=1e-5, atol=1e-6)
     assert abs(out.mean().item() - float(z["mean"])) < 1e-6
+
+
+def test_search_is_cuda_graph_capturable():
+    """Serving loop: the staging + scan + select launches of a small-batch search captured once in a CUDA graph
+    and replayed on new claims (no host-side planning or launches per query batch)."""
+    q, c = _data(16, 200_000, 768, torch.bfloat16, planted=True)
+    static_q = q.clone()
+    drs_b200.search(static_q, c, 10)                                # warm-up: lazy init happens outside the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        s, i = drs_b200.search(static_q, c, 10)
+    for seed in (1, 2):
+        q2, _ = _data(16, 200_000, 768, torch.bfloat16, planted=True, seed=seed)
+        q2 = torch.nn.functional.normalize(c[seed * 100: seed * 100 + 16].float() + 0.05 * q2.float(), dim=1).to(torch.bfloat16)
+        static_q.copy_(q2)
+        graph.replay()
+        torch.cuda.synchronize()
+        es, ei = drs_b200.search(q2, c, 10)
+        assert torch.equal(i, ei) and torch.equal(s, es)
+        assert ei[:, 0].cpu().tolist() == list(range(seed * 100, seed * 100 + 16))
