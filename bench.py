@@ -406,9 +406,9 @@ def run_b200(args):
                 "hbm_frac": ach_gbs / peaks["hbm_gbs"], "mma_frac": ach_tflops / peaks["tflops"],
                 "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": bytes_alg}
 
-    # staging + scan + select on one GPU; sharded: staging + scan + the fused select/exchange/merge kernel (p2p),
-    # or staging + scan + select + merge (nccl)
-    launches_per_step = 3 if (world == 1 or index.exchange == "p2p") else 4
+    # staging + scan + select on one GPU; sharded: staging + scan + the fused select/exchange/merge kernel + its
+    # call-counter bump (p2p), or staging + scan + select + merge (nccl)
+    launches_per_step = 3 if world == 1 else 4
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "claims/s", "n_gpus": world, "steps": args.steps,

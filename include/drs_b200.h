@@ -98,19 +98,22 @@ int drs_search_l2(const void* queries, int64_t nq, const void* corpus, int64_t n
  * claims, acquire/release flags at system scope) for the other shards' lists and merges them.  Replaces the
  * select + 2 x all-gather + merge sequence of the NCCL form; the result is the same on every rank and equal to
  * a single-GPU search of the whole corpus.  (The reference is single-device: nothing upstream to cite.)
- *   peer_scores / peer_ids / peer_flags: HOST arrays of `world` device pointers -- rank r's gather buffers
- *       ([world][nq][k] fp32 and int64) and flag array (drs_exchange_flag_bytes, zeroed once at allocation),
- *       all mapped into this process (cudaIpc / symmetric memory); entry [rank] is this rank's own.
- *   epoch: 1, 2, 3, ... -- the same on all ranks, one more per call on the same buffers.  The caller alternates
- *       between two sets of gather buffers by epoch parity (flags are shared): a rank may run one call ahead
- *       of a peer that is still merging the previous one.
+ *   peer_scores / peer_ids / peer_flags: HOST arrays of `world` device pointers -- rank r's parity-0 gather
+ *       buffers ([world][nq][k] fp32 and int64) and flag array (drs_exchange_flag_bytes, zeroed once at
+ *       allocation), all mapped into this process (cudaIpc / symmetric memory); entry [rank] is this rank's own.
+ *   parity_stride_bytes: distance from a parity-0 gather buffer to its parity-1 twin (a rank may run one call
+ *       ahead of a peer that is still merging the previous one, so calls alternate between two buffer sets).
+ *   call_counter: device uint32 of THIS rank, zero at allocation; the library bumps it once per call and derives
+ *       the call's epoch and buffer parity from it on the device -- no argument changes between calls, so the
+ *       sequence can be captured in a CUDA graph and replayed.
  * All ranks must make the same sequence of calls (it is a collective).  k <= 16, world <= 8.
  */
 int drs_exchange_flag_bytes(int64_t max_nq, int world, size_t* bytes);
 int drs_search_sharded_p2p(const void* queries, int64_t nq, const void* corpus, int64_t nc_local, int dim, int dtype,
                            int k, int64_t id_base, int rank, int world, void* const* peer_scores,
-                           void* const* peer_ids, void* const* peer_flags, uint32_t epoch, float* out_scores,
-                           int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream);
+                           void* const* peer_ids, void* const* peer_flags, size_t parity_stride_bytes,
+                           uint32_t* call_counter, float* out_scores, int64_t* out_ids, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /*
  * Candidate-restricted re-rank: score each claim against ITS OWN candidate rows only and keep the best k.

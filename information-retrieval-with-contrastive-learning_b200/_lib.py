@@ -39,7 +39,7 @@ _SIGNATURES = {
                                        c_sz, c_vp]),
     "drs_exchange_flag_bytes": (c_int, [c_i64, c_int, ctypes.POINTER(c_sz)]),
     "drs_search_sharded_p2p": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_vp,
-                                       ctypes.c_uint32, c_vp, c_vp, c_vp, c_sz, c_vp]),
+                                       c_sz, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "drs_merge_shards": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp]),
     "drs_infonce_workspace_bytes": (c_int, [c_i64, c_int, c_i64, c_int, ctypes.POINTER(c_sz)]),
     "drs_infonce_forward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_f32, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -16,8 +16,9 @@
 //   3. wait: ld.acquire.sys until all `world` flags of this claim block show the epoch -- the lists
 //      of this block have arrived from every shard (no global barrier: blocks proceed independently);
 //   4. merge: the warp orders the world * k candidates by (score desc, id asc) and writes the result.
-// Flags carry a monotonically increasing epoch and are never reset, so there is no cleanup pass and
-// a change of batch size between calls is harmless.  The gather buffers are double-buffered by
+// Flags carry a monotonically increasing epoch (a per-rank device counter of completed calls, so a captured
+// CUDA graph replays correctly) and are never reset, so there is no cleanup pass and a change of batch size
+// between calls is harmless.  The gather buffers are double-buffered by
 // epoch parity: a rank can be at most one call ahead of its slowest peer (it cannot finish call n+1
 // before every peer has published call n+1, i.e. finished reading call n).
 // All CTAs are co-resident (grid <= resident capacity) and every block publishes before it waits,
@@ -35,9 +36,11 @@ enum : uint32_t { kTagExchangeWait = 6 };
 static constexpr long long kExchangeTimeoutCycles = 180000000000LL;
 
 struct ExchangePeers {
-  float* scores[kMaxPeers];     // rank p's gather buffer: [world][nq][k] fp32   (peer-mapped pointers)
-  long long* ids[kMaxPeers];    //                         [world][nq][k] int64
-  uint32_t* flags[kMaxPeers];   // rank p's flags:         [claim blocks][world]
+  float* scores[kMaxPeers];     // rank p's gather buffers, parity 0: [world][nq][k] fp32   (peer-mapped pointers)
+  long long* ids[kMaxPeers];    //                                    [world][nq][k] int64
+  uint32_t* flags[kMaxPeers];   // rank p's flags:                    [claim blocks][world]
+  size_t parity_stride;         // bytes from a parity-0 buffer to its parity-1 twin (same for scores and ids)
+  const uint32_t* calls;        // this rank's device counter of completed exchange calls: epoch = *calls + 1
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
@@ -56,9 +59,19 @@ constexpr int kExchangeRowsPerBlock = 8;  // 8 warps, one claim each
 template <int SL>
 __global__ void __launch_bounds__(256)
 select_exchange_merge_kernel(const uint64_t* __restrict__ ws, int nq, int nslots, int kcap, int k, long long id_base,
-                             const ExchangePeers peers, int rank, int world, uint32_t epoch,
+                             ExchangePeers peers, int rank, int world,
                              float* __restrict__ out_scores, long long* __restrict__ out_ids) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // The epoch lives on the device (bumped by exchange_done_kernel after this kernel), so the call sequence can be
+  // captured in a CUDA graph and replayed: no launch argument changes from call to call.
+  const uint32_t epoch = *peers.calls + 1u;
+  if (epoch & 1u) {
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p) {
+      peers.scores[p] = reinterpret_cast<float*>(reinterpret_cast<char*>(peers.scores[p]) + peers.parity_stride);
+      peers.ids[p] = reinterpret_cast<long long*>(reinterpret_cast<char*>(peers.ids[p]) + peers.parity_stride);
+    }
+  }
   const int num_blocks = (nq + kExchangeRowsPerBlock - 1) / kExchangeRowsPerBlock;
   const size_t slot = static_cast<size_t>(nq) * k;  // one rank's [nq][k] list
   for (int rb = blockIdx.x; rb < num_blocks; rb += gridDim.x) {
@@ -162,5 +175,8 @@ select_exchange_merge_kernel(const uint64_t* __restrict__ ws, int nq, int nslots
     }
   }
 }
+
+// One more exchange call is complete on this rank (stream-ordered after select_exchange_merge_kernel).
+__global__ void exchange_done_kernel(uint32_t* calls) { *calls += 1u; }
 
 }  // namespace drs

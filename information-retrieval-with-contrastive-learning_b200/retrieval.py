@@ -421,16 +421,13 @@ class _PeerExchange:
         self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
         self.handle.barrier()                         # every rank's flags are zero before anyone publishes
         self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        self.epoch = 0
-
-    def pointer_arrays(self):
-        """(epoch, scores[world], ids[world], flags[world]) as ctypes arrays for the next call."""
-        self.epoch += 1
-        par = self.epoch & 1
-        base = self.flag_bytes + par * (self.s_bytes + self.i_bytes)
-        arr = ctypes.c_void_p * self.world
-        return (self.epoch, arr(*[p + base for p in self.ptrs]), arr(*[p + base + self.s_bytes for p in self.ptrs]),
-                arr(*self.ptrs))
+        self.calls = torch.zeros(1, dtype=torch.int32, device=device)      # this rank's completed exchange calls
+        arr = ctypes.c_void_p * world
+        base = self.flag_bytes                                             # parity-0 buffers; parity 1 = + parity_stride
+        self.parity_stride = self.s_bytes + self.i_bytes
+        self.score_ptrs = arr(*[p + base for p in self.ptrs])
+        self.id_ptrs = arr(*[p + base + self.s_bytes for p in self.ptrs])
+        self.flag_ptrs = arr(*self.ptrs)
 
 
 class ShardedDenseIndex:
@@ -531,13 +528,13 @@ class ShardedDenseIndex:
             scores = torch.empty(nq, kk, dtype=torch.float32, device=dev)
             ids = torch.empty(nq, kk, dtype=torch.int64, device=dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            epoch, ps, pi, pf = peer.pointer_arrays()
             ev0 = ev1 = None
             if profile is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
             _lib.check(lib.drs_search_sharded_p2p(q.data_ptr(), nq, loc.embeddings.data_ptr(), nc, dim, dt, kk, loc.id_base,
-                                                  self.rank, self.world, ps, pi, pf, epoch, scores.data_ptr(),
+                                                  self.rank, self.world, peer.score_ptrs, peer.id_ptrs, peer.flag_ptrs,
+                                                  peer.parity_stride, peer.calls.data_ptr(), scores.data_ptr(),
                                                   ids.data_ptr(), ws.data_ptr(), ws.numel(), stream))
             if profile is not None:
                 ev1.record()

@@ -48,6 +48,34 @@ for nq, nc, dim, k in [(300, 100003, 128, 10), (1000, 1000000, 768, 10), (64, 7,
               f"tie={tie_ok} all_ranks={bool(flag.item())}", flush=True)
     ok = ok and bool(flag.item())
 
+# the fused exchange keeps its epoch on the device: a captured CUDA graph of the sharded search replays correctly
+nc, dim, k = 200_000, 128, 10
+g = torch.Generator(device=dev).manual_seed(99)
+corpus = torch.nn.functional.normalize(torch.randn(nc, dim, generator=g, device=dev), dim=1).bfloat16()
+lo, hi = drs_b200.shard_bounds(nc, rank, world)
+idx = drs_b200.ShardedDenseIndex(corpus[lo:hi].clone(), nc, device=dev)
+static_q = corpus[:16].clone()
+for _ in range(2):
+    idx.search(static_q, k)
+torch.cuda.synchronize()
+dist.barrier()
+graph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(graph):
+    gs, gi = idx.search(static_q, k)
+graph_ok = idx.exchange == "p2p"
+for rep in range(4):
+    static_q.copy_(corpus[1000 * rep + 7: 1000 * rep + 23])
+    graph.replay()
+    torch.cuda.synchronize()
+    graph_ok = graph_ok and gi[:, 0].tolist() == list(range(1000 * rep + 7, 1000 * rep + 23))
+es, ei = idx.search(static_q, k)                                   # eager calls interleave with replays
+graph_ok = graph_ok and torch.equal(ei, gi) and torch.equal(es, gs)
+flag = torch.tensor([int(graph_ok)], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"sharded x{world} [{idx.exchange}] CUDA graph replay of the fused exchange: {bool(flag.item())}", flush=True)
+ok = ok and bool(flag.item())
+
 # latency of the exchange in the small-batch regime: fused p2p kernel vs select + 2 all-gathers + merge
 nc, dim, k = 4_000_000, 768, 10
 g = torch.Generator(device=dev).manual_seed(1337 + rank)
