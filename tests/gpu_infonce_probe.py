@@ -60,3 +60,46 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def reference_config():
+    """The reference's own training shapes (config.yaml: batch 128, output 128, queue 12544, T 0.05)."""
+    n, dim, klen = 128, 128, 12544
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(7)
+    q = torch.nn.functional.normalize(torch.randn(n, dim, generator=g, device=dev), dim=1).requires_grad_(True)
+    k = torch.nn.functional.normalize(torch.randn(n, dim, generator=g, device=dev), dim=1).requires_grad_(True)
+    queue = torch.nn.functional.normalize(torch.randn(dim, klen, generator=g, device=dev), dim=0)
+    crit = drs.NCELoss({"temperature": 0.05})
+
+    def step():
+        q.grad = None
+        k.grad = None
+        crit(q, k, queue).backward()
+
+    def torch_step():
+        q.grad = None
+        k.grad = None
+        f = torch.cat([q, k])
+        s = f @ f.T
+        s = s.masked_fill(torch.eye(2 * n, dtype=torch.bool, device=dev), float("-inf"))
+        lq = (q @ queue).repeat(2, 1)
+        logits = torch.cat([s, lq], dim=1) / 0.05
+        tgt = (torch.arange(2 * n, device=dev) + n) % (2 * n)
+        (torch.nn.functional.cross_entropy(logits, tgt, reduction="sum") / 2).backward()
+
+    for name, fn in (("drs_b200 NCELoss", step), ("torch closed form", torch_step)):
+        for _ in range(10):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(100):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"reference config (N=128, D=128, queue 12544) {name}: {e0.elapsed_time(e1) / 100 * 1e3:.1f} us/step")
+
+
+if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "refcfg":
+    reference_config()
