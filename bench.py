@@ -193,8 +193,11 @@ def bench_other_configs(torch, drs_b200, dev, peaks, shard, queries, rank, world
     c32 = shard[:100_000].float()
     q32 = queries[:1000].float()
     ms = timed(lambda: drs_b200.search(q32, c32, 5), 5)
+    tf32 = 2.0 * 1000 * 100_000 * dim / (ms * 1e-3) / 1e12
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    ffma_roof = sms * 64 * 2 * 1.965e9 / 1e12      # a 3-register FFMA issues every 2 cycles per SM sub-partition: 64 FMA/clk/SM
     rec = {"workload": "1000 claims x 100000 x 768 fp32, top-5 (exact FFMA path)", "ms_per_step": ms,
-           "claims_per_s": 1000 / (ms * 1e-3), "tflops_fp32": 2.0 * 1000 * 100_000 * dim / (ms * 1e-3) / 1e12}
+           "claims_per_s": 1000 / (ms * 1e-3), "tflops_fp32": tf32, "ffma_roof_tflops": ffma_roof, "ffma_frac": tf32 / ffma_roof}
     if rank == 0:
         from oracle import dense_topk
         qc, cc = q32.cpu(), c32.cpu()
