@@ -25,7 +25,7 @@ extern "C" {
 #endif
 
 enum { DRS_OK = 0, DRS_ERR_INVALID = 1, DRS_ERR_CUDA = 2, DRS_ERR_UNSUPPORTED = 3, DRS_ERR_WORKSPACE = 4 };
-enum { DRS_F32 = 0, DRS_BF16 = 1 };
+enum { DRS_F32 = 0, DRS_BF16 = 1, DRS_F16 = 2 };  /* DRS_F16: IEEE half operands on the same tcgen05 path as DRS_BF16 */
 #define DRS_MAX_K 256  /* k > 16: adaptive passes over the corpus (at most ceil(k/16), usually one) */
 
 int drs_version(void);
@@ -51,11 +51,11 @@ int drs_debug_max_clusters(int cluster_size, int* out);
  * (preprocessing/drqa/retriever/tfidf_doc_ranker.py:60-75), batched over claims like
  * batch_closest_docs (:77-84).
  *
- *   queries  device [nq, dim]   dtype DRS_BF16 (tcgen05 path) or DRS_F32 (exact FFMA path)
+ *   queries  device [nq, dim]   dtype DRS_BF16 / DRS_F16 (tcgen05 path, fp32 accumulate) or DRS_F32 (exact FFMA path)
  *   corpus   device [nc, dim]   same dtype
  *   out_scores device [nq, k] fp32, descending;  out_ids device [nq, k] int64 = row + id_base
  *   ties are broken by the lower row index; when nc < k the tail is (-inf, -1).
- * DRS_BF16 needs dim % 8 == 0 and 16-byte aligned base pointers (TMA); k <= DRS_MAX_K.
+ * DRS_BF16 / DRS_F16 need dim % 8 == 0 and 16-byte aligned base pointers (TMA); k <= DRS_MAX_K.
  * The running top-k lists hold 16 (or, for 17 <= k on corpora with few splits, 32) entries per (claim, corpus
  * split) in registers.  k beyond the list capacity stays exact: the select emits picks only while no
  * split's full list could hide a better row, and a claim that stops early is continued by a rescan strictly

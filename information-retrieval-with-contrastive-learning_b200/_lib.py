@@ -10,7 +10,7 @@ import threading
 
 from . import build as _build
 
-DRS_F32, DRS_BF16 = 0, 1
+DRS_F32, DRS_BF16, DRS_F16 = 0, 1, 2
 DRS_MAX_K = 256
 
 _lock = threading.Lock()

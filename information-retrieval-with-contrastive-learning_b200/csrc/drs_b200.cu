@@ -109,14 +109,16 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 // [rows, dim] bf16 row-major; box = 64 (K) x box_rows, 128-byte swizzle, zero fill out of bounds
-int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int dim, int box_rows) {
+inline bool is_16bit(int dtype) { return dtype == DRS_BF16 || dtype == DRS_F16; }
+
+int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int dim, int box_rows, bool f16 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(DRS_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim) * 2};
   cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(DRS_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
@@ -161,6 +163,7 @@ drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int 
   s.stagger_cycles = g_opt.stagger_cycles;
   s.round_counter = nullptr;
   s.active = nullptr;
+  s.f16_operands = 0;
   return s;
 }
 
@@ -197,7 +200,7 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
   if (int rc = get_device_info(&di)) return rc;
   p->dtype = dtype;
   p->k = k;
-  if (dtype == DRS_BF16) {
+  if (is_16bit(dtype)) {
     if (di.cc_major != 10) return fail(DRS_ERR_UNSUPPORTED, "the bf16 path needs an sm_100 device (tcgen05/TMEM); this is sm_%d%d", di.cc_major, di.cc_minor);
     if (dim % 8 != 0) return fail(DRS_ERR_INVALID, "bf16 path: dim must be a multiple of 8 (TMA 16-byte row pitch), got %d", dim);
     // CTA pair (256-row A tiles) for large batches; single CTAs (128-row tiles) up to 128 claims, and near the
@@ -215,6 +218,7 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
     p->cg = cg;
     p->grid = ctas;
     p->shape = plan_shape(nq, nc, (dim + 63) / 64, 128 * cg, 256, ctas / cg, g_opt.splits, kTcColGroups);
+    p->shape.f16_operands = dtype == DRS_F16;
   } else if (dtype == DRS_F32) {
     int ctas = g_opt.num_ctas > 0 ? g_opt.num_ctas : 2 * di.num_sms;
     p->cg = 1;
@@ -239,7 +243,7 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
   p->cand_bytes = align256s(static_cast<size_t>(nq) * num_slots(p->shape) * p->kcap * sizeof(uint64_t));
   p->pad_bytes = 0;
   p->a_rows = nq;
-  if (dtype == DRS_BF16) {
+  if (is_16bit(dtype)) {
     // TMA boxes that hang over the end of the claims matrix are zero-filled correctly but SLOWLY (measured:
     // 1 claim in a 128-row box streams the corpus at 4.7 TB/s, the same claim zero-padded in memory at
     // 6.7 TB/s), and with the round barrier one slow A tile holds every cluster back.  Stage a padded copy.
@@ -267,8 +271,8 @@ int launch_gemm_tc(const void* a, const void* b, int kdim, const drs::GemmShape&
                    const typename Epi::Params& ep, cudaStream_t st, int64_t a_rows_alloc = 0) {
   using Cfg = drs::GemmCfg<CG, BN>;
   CUtensorMap ta, tb;
-  if (int rc = make_tmap_bf16(&ta, a, a_rows_alloc > 0 ? a_rows_alloc : shp.rows_a, kdim, Cfg::BM)) return rc;
-  if (int rc = make_tmap_bf16(&tb, b, shp.rows_b, kdim, Cfg::BN_CTA)) return rc;
+  if (int rc = make_tmap_bf16(&ta, a, a_rows_alloc > 0 ? a_rows_alloc : shp.rows_a, kdim, Cfg::BM, shp.f16_operands != 0)) return rc;
+  if (int rc = make_tmap_bf16(&tb, b, shp.rows_b, kdim, Cfg::BN_CTA, shp.f16_operands != 0)) return rc;
   auto kern = drs::gemm_nt_tc_kernel<CG, Epi, BN>;
   DRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   cudaLaunchConfig_t cfg;
@@ -473,13 +477,13 @@ int scan_pass(SearchPlan& p, const void* queries, const void* corpus, int dim, v
   // seeds pay only when a claim's units run one after another: with a single round (units <= groups, e.g. one A
   // tile split 148 ways) nobody ever reads them, and 296 lists publishing for the same 128 claims at the same
   // moment contend on the compare-and-swap (measured +100 us on a 370 us scan)
-  const int groups = p.dtype == DRS_BF16 ? p.grid / p.cg : p.grid;
+  const int groups = is_16bit(p.dtype) ? p.grid / p.cg : p.grid;
   if (g_opt.seed_thresholds && p.shape.num_splits > 1 && p.shape.num_m_tiles * p.shape.num_splits > groups)
     seeds = reinterpret_cast<uint32_t*>(base + kWsHeaderBytes + p.bound_bytes + extra_bytes + p.cand_bytes + p.pad_bytes);
   uint64_t* ws = reinterpret_cast<uint64_t*>(base + kWsHeaderBytes + p.bound_bytes + extra_bytes);
   p.shape.round_counter = nullptr;
   char* pad = nullptr;
-  if (p.dtype == DRS_BF16) {
+  if (is_16bit(p.dtype)) {
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
     if (g_opt.round_barrier && p.grid <= di.num_sms)   // all CTAs co-resident: the barrier cannot deadlock
@@ -499,7 +503,7 @@ int scan_pass(SearchPlan& p, const void* queries, const void* corpus, int dim, v
     DRS_CUDA(cudaGetLastError());
     if (pad) queries = pad;
   }
-  if (p.dtype == DRS_BF16) {
+  if (is_16bit(p.dtype)) {
     if (p.cg == 1) return p.kcap == 16 ? launch_search_tc<1, 16>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, seeds, st)
                                        : launch_search_tc<1, 32>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, seeds, st);
     return p.kcap == 16 ? launch_search_tc<2, 16>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, seeds, st)
@@ -514,7 +518,7 @@ int check_search_args(const SearchPlan& p, const void* queries, const void* corp
   if (!workspace || workspace_bytes < p.ws_bytes)
     return fail(DRS_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", p.ws_bytes, workspace_bytes);
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(DRS_ERR_INVALID, "workspace must be 256-byte aligned");
-  if (p.dtype == DRS_BF16 && ((reinterpret_cast<uintptr_t>(queries) & 15) || (reinterpret_cast<uintptr_t>(corpus) & 15)))
+  if (is_16bit(p.dtype) && ((reinterpret_cast<uintptr_t>(queries) & 15) || (reinterpret_cast<uintptr_t>(corpus) & 15)))
     return fail(DRS_ERR_INVALID, "bf16 path: queries and corpus must be 16-byte aligned");
   return DRS_OK;
 }
@@ -616,7 +620,10 @@ int drs_search_l2(const void* queries, int64_t nq, const void* corpus, int64_t n
   float* col_bias = reinterpret_cast<float*>(base + kWsHeaderBytes + p.bound_bytes);
   float* row_term = reinterpret_cast<float*>(base + kWsHeaderBytes + p.bound_bytes + align256s(nc * sizeof(float)));
   const int bc = static_cast<int>((nc + 7) / 8), bq = static_cast<int>((nq + 7) / 8);
-  if (dtype == DRS_BF16) {
+  if (dtype == DRS_F16) {
+    drs::row_sqnorm_kernel<__half><<<bc, 256, 0, st>>>(static_cast<const __half*>(corpus), nc, dim, -1.f, col_bias);
+    drs::row_sqnorm_kernel<__half><<<bq, 256, 0, st>>>(static_cast<const __half*>(queries), nq, dim, 1.f, row_term);
+  } else if (dtype == DRS_BF16) {
     drs::row_sqnorm_kernel<__nv_bfloat16><<<bc, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(corpus), nc, dim, -1.f, col_bias);
     drs::row_sqnorm_kernel<__nv_bfloat16><<<bq, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(queries), nq, dim, 1.f, row_term);
   } else {

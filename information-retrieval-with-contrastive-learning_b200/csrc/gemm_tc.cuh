@@ -38,6 +38,7 @@ struct GemmShape {
   int stagger_cycles;   // producer start delay per A-tile index (experiment knob)
   unsigned int* round_counter;  // zeroed device counter for the per-round producer barrier, or nullptr
   const unsigned int* active;   // optional: the whole launch is a no-op when *active == 0 (adaptive k > 32 passes)
+  int f16_operands;             // 0: bf16 operands, 1: IEEE half operands (same kind::f16 MMA, other instruction descriptor)
 };
 
 // BN_ = 256 is the only width instantiated: 128-wide tiles were tried for the GEMM with few B tiles (dF = H F) and
@@ -176,7 +177,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one thread, leader CTA)
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(128 * CG, Cfg::BN);
+      const uint32_t idesc = shp.f16_operands ? make_idesc_f16_f32(128 * CG, Cfg::BN) : make_idesc_bf16_f32(128 * CG, Cfg::BN);
       uint32_t stage = 0, phase = 0, it = 0;
       for (int u = cluster; u < num_units; u += nclusters) {
         const int s = u / shp.num_m_tiles;

@@ -4,6 +4,7 @@
 // than the previous pick" walks the order without mutating the candidate set.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "topk.cuh"
 

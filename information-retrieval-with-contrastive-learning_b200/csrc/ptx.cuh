@@ -193,6 +193,10 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
+// Same, IEEE half operands (A/B format 0).
+__host__ __device__ constexpr uint32_t make_idesc_f16_f32(uint32_t m, uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
 // kind::tf32: fp32 operands read as tf32 (A/B format 2), fp32 accumulate.
 __host__ __device__ constexpr uint32_t make_idesc_tf32_f32(uint32_t m, uint32_t n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);

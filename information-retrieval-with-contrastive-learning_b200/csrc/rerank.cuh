@@ -10,6 +10,7 @@
 // in the same block from packed (score, ~id) keys -- the score list never reaches memory.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "merge.cuh"
 
@@ -32,6 +33,20 @@ template <> struct RowVec<__nv_bfloat16> {
     for (int i = 0; i < 4; ++i) {  // bf16 -> fp32 is a 16-bit shift
       v[2 * i] = __uint_as_float(w[i] << 16);
       v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+
+template <> struct RowVec<__half> {
+  static constexpr int W = 8;
+  static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
     }
   }
 };

@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 
-_DTYPES = {torch.float32: _lib.DRS_F32, torch.bfloat16: _lib.DRS_BF16}
+_DTYPES = {torch.float32: _lib.DRS_F32, torch.bfloat16: _lib.DRS_BF16, torch.float16: _lib.DRS_F16}
 
 # one cached workspace per (device, stream) so steady-state searches allocate nothing
 _workspaces: dict = {}
@@ -39,7 +39,7 @@ def _check_matrix(name: str, t: torch.Tensor):
     if not isinstance(t, torch.Tensor) or t.dim() != 2:
         raise ValueError(f"{name} must be a 2-D tensor, got {type(t).__name__} with shape {getattr(t, 'shape', None)}")
     if t.dtype not in _DTYPES:
-        raise TypeError(f"{name} must be float32 or bfloat16, got {t.dtype}")
+        raise TypeError(f"{name} must be float32, bfloat16 or float16, got {t.dtype}")
     if not t.is_cuda:
         raise RuntimeError(f"{name} must live on a CUDA device: drs_b200 has no CPU path")
 
@@ -47,8 +47,8 @@ def _check_matrix(name: str, t: torch.Tensor):
 def search(queries: torch.Tensor, corpus: torch.Tensor, k: int, *, id_base: int = 0, profile: Optional[list] = None):
     """Top-k corpus rows per query by dot product.
 
-    queries [nq, D], corpus [Nc, D]: CUDA, row-major, same dtype (bf16 -> tcgen05 path, scores
-    within 2e-2 relative of fp32; fp32 -> exact FFMA path, 1e-5).  Rows are expected to be
+    queries [nq, D], corpus [Nc, D]: CUDA, row-major, same dtype (bf16 or fp16 -> tcgen05 path, fp32
+    accumulation, scores within 2e-2 relative of fp32; fp32 -> exact FFMA path, 1e-5).  Rows are expected to be
     L2-normalised the way ``seq2vec`` does (src/contrastor/contrastive_module.py:111), so the dot
     product is the cosine; nothing here depends on that.
 

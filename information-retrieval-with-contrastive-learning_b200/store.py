@@ -28,8 +28,8 @@ import torch
 MAGIC = b"DRSIDX01"
 HEADER_BYTES = 4096
 _HEADER = struct.Struct("<8sIIqqqqqI")   # magic, version, dtype, rows, dim, payload_off, payload_bytes, meta_bytes, crc32
-_DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1}
-_CODE_DTYPES = {0: (torch.float32, np.float32, 4), 1: (torch.bfloat16, np.uint16, 2)}
+_DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+_CODE_DTYPES = {0: (torch.float32, np.float32, 4), 1: (torch.bfloat16, np.uint16, 2), 2: (torch.float16, np.float16, 2)}
 
 
 def _as_raw(t: torch.Tensor) -> np.ndarray:
@@ -46,7 +46,7 @@ def save_dense_index(filename: str, embeddings: torch.Tensor, metadata: Optional
     if embeddings.dim() != 2:
         raise ValueError("embeddings must be [rows, dim]")
     if dtype not in _DTYPE_CODES:
-        raise TypeError("dtype must be torch.bfloat16 or torch.float32")
+        raise TypeError("dtype must be torch.bfloat16, torch.float16 or torch.float32")
     rows, dim = embeddings.shape
     esize = _CODE_DTYPES[_DTYPE_CODES[dtype]][2]
     meta = pickle.dumps(metadata, protocol=4)

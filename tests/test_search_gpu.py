@@ -431,3 +431,26 @@ def test_search_is_cuda_graph_capturable():
         es, ei = drs_b200.search(q2, c, 10)
         assert torch.equal(i, ei) and torch.equal(s, es)
         assert ei[:, 0].cpu().tolist() == list(range(seed * 100, seed * 100 + 16))
+
+
+@pytest.mark.parametrize("nq,nc,dim,k", [(64, 5000, 128, 5), (300, 40000, 768, 10), (1000, 30000, 256, 100)])
+def test_fp16_operands_on_the_tensor_core_path(nq, nc, dim, k):
+    """IEEE half embeddings (DRS_F16): same tcgen05 kernel with the f16 instruction descriptor; the oracle takes
+    the same fp16 values upcast to fp32.  Also through the squared-L2 epilogue, the re-rank and the pair score."""
+    q, c = _data(nq, nc, dim, torch.float16, planted=True)
+    s, i = drs_b200.search(q, c, k)
+    _check(q, c, k, s, i, score_rtol=2e-2, gap=1e-4)
+    d, li = drs_b200.flat_l2_search(q[:50], c, 1)
+    rd, rli = dense_topk.flat_l2_search(q[:50].cpu(), c.cpu(), 1)
+    assert torch.equal(li.cpu(), rli)
+    torch.testing.assert_close(d.cpu(), rd, rtol=2e-2, atol=2e-3)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    cand = torch.randint(0, nc, (nq, 50), generator=g, device=DEV)
+    rs, ri = drs_b200.rerank(q, c, cand, 5)
+    os_, oi = dense_topk.rerank(q.cpu(), c.cpu(), cand.cpu(), 5)
+    torch.testing.assert_close(rs.cpu(), os_, rtol=1e-4, atol=1e-5)
+    assert torch.equal(ri.cpu()[:, 0], oi[:, 0])
+    torch.testing.assert_close(drs_b200.paired_scores(q, c[:nq]).cpu(), dense_topk.paired_scores(q.cpu(), c[:nq].cpu()),
+                               rtol=1e-4, atol=1e-5)
+    idx = drs_b200.DenseIndex(c, dtype=torch.float16)
+    assert idx.embeddings.dtype == torch.float16 and torch.equal(idx.search(q, k)[1], i)

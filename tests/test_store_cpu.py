@@ -11,7 +11,7 @@ from importlib import import_module
 store = import_module(drs_b200.__name__ + ".store")
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32, torch.float16])
 def test_round_trip_rows_ranges_and_metadata(tmp_path, dtype):
     g = torch.Generator().manual_seed(1337)
     emb = torch.nn.functional.normalize(torch.randn(1000, 96, generator=g), dim=1)
