@@ -114,6 +114,7 @@ struct TopKEpilogue {
       const bool hit = (s > list.thr) && (make_key(s, static_cast<uint32_t>(col0 + j)) < bnd);
       list.insert(hit ? s : -INFINITY, static_cast<uint32_t>(col0 + j), p.k);
     }
+    __syncwarp();  // lanes leave the loop at different times; the caller's next tcgen05.ld is .sync.aligned
   }
 
   __device__ __forceinline__ void end_unit(const Params& p, int row, int, int slot) {

@@ -231,6 +231,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll 1
         for (int c = 0; c < Cfg::CHUNKS_PER_GROUP; ++c) {
           uint32_t v[32];
+          __syncwarp();  // the functor (and the barrier wait) may leave lanes diverged; tcgen05.ld is .sync.aligned
           if (!(shp.debug_flags & 2)) {
             tmem_ld_32x32b_x32(taddr + c * 32, v);  // includes tcgen05.wait::ld
           } else {
