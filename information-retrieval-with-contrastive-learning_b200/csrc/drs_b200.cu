@@ -59,6 +59,7 @@ struct Options {
   int stagger_cycles = 0;
   int round_barrier = 1;
   int seed_thresholds = 1;
+  int symmetric_grad = 1;
 } g_opt;
 
 struct DeviceInfo {
@@ -164,6 +165,7 @@ drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int 
   s.round_counter = nullptr;
   s.active = nullptr;
   s.f16_operands = 0;
+  s.skip_below_diagonal = 0;
   return s;
 }
 
@@ -440,6 +442,7 @@ int drs_set_option(const char* name, int value) {
   else if (!strcmp(name, "tune.stagger_cycles")) g_opt.stagger_cycles = value;
   else if (!strcmp(name, "tune.round_barrier")) g_opt.round_barrier = value;
   else if (!strcmp(name, "tune.seed_thresholds")) g_opt.seed_thresholds = value;
+  else if (!strcmp(name, "tune.symmetric_grad")) g_opt.symmetric_grad = value;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;
 }
@@ -454,6 +457,7 @@ int drs_get_option(const char* name, int* value) {
   else if (!strcmp(name, "tune.stagger_cycles")) *value = g_opt.stagger_cycles;
   else if (!strcmp(name, "tune.round_barrier")) *value = g_opt.round_barrier;
   else if (!strcmp(name, "tune.seed_thresholds")) *value = g_opt.seed_thresholds;
+  else if (!strcmp(name, "tune.symmetric_grad")) *value = g_opt.symmetric_grad;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;
 }

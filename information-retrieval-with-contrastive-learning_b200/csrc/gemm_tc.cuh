@@ -39,6 +39,29 @@ struct GemmShape {
   unsigned int* round_counter;  // zeroed device counter for the per-round producer barrier, or nullptr
   const unsigned int* active;   // optional: the whole launch is a no-op when *active == 0 (adaptive k > 32 passes)
   int f16_operands;             // 0: bf16 operands, 1: IEEE half operands (same kind::f16 MMA, other instruction descriptor)
+  int skip_below_diagonal;      // A == B, square (A tile rows == B tile rows), symmetric output: only the tiles on and
+                                // above the diagonal are computed, dealt to the clusters as contiguous pieces of the
+                                // row-major triangle (TriangleWalk); the epilogue writes both halves
+};
+
+// The tiles on and above the diagonal of a square tile grid (t >= m), row-major, cut into `parts` contiguous,
+// equally long pieces: piece `part` walks its share.  Consecutive tiles mostly share the A tile (m).
+struct TriangleWalk {
+  int m, t, left, tiles_m;
+  __device__ TriangleWalk(int num_m_tiles, unsigned part, unsigned parts) : tiles_m(num_m_tiles) {
+    const long long live = static_cast<long long>(num_m_tiles) * (num_m_tiles + 1) / 2;
+    long long lo = live * part / parts;
+    const long long hi = live * (part + 1) / parts;
+    left = static_cast<int>(hi - lo);
+    m = 0;
+    while (m < num_m_tiles && lo >= num_m_tiles - m) { lo -= num_m_tiles - m; ++m; }
+    t = m + static_cast<int>(lo);
+  }
+  __device__ bool valid() const { return left > 0; }
+  __device__ void next() {
+    --left;
+    if (++t == tiles_m) { ++m; t = m; }
+  }
 };
 
 // BN_ = 256 is the only width instantiated: 128-wide tiles were tried for the GEMM with few B tiles (dF = H F) and
@@ -135,43 +158,48 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       // and each B tile is fetched from HBM once per round instead of once per straggler (without
       // it the groups drift apart by more than the L2 can hold and the corpus is re-read ~18x).
       // All CTAs are co-resident (grid <= SM count, one CTA per SM), so the spin cannot deadlock.
-      const int num_rounds = (num_units + static_cast<int>(nclusters) - 1) / static_cast<int>(nclusters);
-      for (int round = 0; round < num_rounds; ++round) {
-        const int u = static_cast<int>(cluster) + round * static_cast<int>(nclusters);
-        if (shp.round_counter != nullptr && round > 0) {
-          const unsigned int target = static_cast<unsigned int>(round) * gridDim.x;
-          const long long t_start = clock64();
-          while (ld_acquire_gpu_u32(shp.round_counter) < target) {
-            __nanosleep(64);
-            if (clock64() - t_start > kMbarTimeoutCycles) mbar_hang(kTagRoundBarrier, round, target);
+      auto load_tile = [&](int m, int t) {
+        const int row_a = (m * CG + static_cast<int>(cta_rank)) * Cfg::BM;
+        const int row_b = t * Cfg::BN + static_cast<int>(cta_rank) * Cfg::BN_CTA;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u, kTagProducerEmpty, stage);
+          void* dst_a = smem_a + stage * Cfg::A_BYTES;
+          void* dst_b = smem_b + stage * Cfg::B_BYTES;
+          if constexpr (CG == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(dst_a, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
+            tma_load_2d(dst_b, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, hint_b);
+          } else {
+            tma_load_2d_pair(dst_a, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
+            tma_load_2d_pair(dst_b, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, hint_b);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            else mbar_arrive_cluster(&full_bar[stage], 0);
           }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (u < num_units) {
-          const int m = u % shp.num_m_tiles, s = u / shp.num_m_tiles;
-          const int t0 = s * shp.tiles_per_split;
-          const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
-          const int row_a = (m * CG + static_cast<int>(cta_rank)) * Cfg::BM;
-          for (int t = t0; t < t1; ++t) {
-            const int row_b = t * Cfg::BN + static_cast<int>(cta_rank) * Cfg::BN_CTA;
-            for (int kb = 0; kb < nkb; ++kb) {
-              mbar_wait(&empty_bar[stage], phase ^ 1u, kTagProducerEmpty, stage);
-              void* dst_a = smem_a + stage * Cfg::A_BYTES;
-              void* dst_b = smem_b + stage * Cfg::B_BYTES;
-              if constexpr (CG == 1) {
-                mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                tma_load_2d(dst_a, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
-                tma_load_2d(dst_b, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, hint_b);
-              } else {
-                tma_load_2d_pair(dst_a, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
-                tma_load_2d_pair(dst_b, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, hint_b);
-                if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                else mbar_arrive_cluster(&full_bar[stage], 0);
-              }
-              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+      };
+      if (shp.skip_below_diagonal) {
+        for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters); w.valid(); w.next()) load_tile(w.m, w.t);
+      } else {
+        const int num_rounds = (num_units + static_cast<int>(nclusters) - 1) / static_cast<int>(nclusters);
+        for (int round = 0; round < num_rounds; ++round) {
+          const int u = static_cast<int>(cluster) + round * static_cast<int>(nclusters);
+          if (shp.round_counter != nullptr && round > 0) {
+            const unsigned int target = static_cast<unsigned int>(round) * gridDim.x;
+            const long long t_start = clock64();
+            while (ld_acquire_gpu_u32(shp.round_counter) < target) {
+              __nanosleep(64);
+              if (clock64() - t_start > kMbarTimeoutCycles) mbar_hang(kTagRoundBarrier, round, target);
             }
           }
+          if (u < num_units) {
+            const int m = u % shp.num_m_tiles, s = u / shp.num_m_tiles;
+            const int t0 = s * shp.tiles_per_split;
+            const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
+            for (int t = t0; t < t1; ++t) load_tile(m, t);
+          }
+          if (shp.round_counter != nullptr) red_release_gpu_add_u32(shp.round_counter, 1u);
         }
-        if (shp.round_counter != nullptr) red_release_gpu_add_u32(shp.round_counter, 1u);
       }
     }
   } else if (warp == 1) {
@@ -179,31 +207,37 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (lane == 0 && leader) {
       const uint32_t idesc = shp.f16_operands ? make_idesc_f16_f32(128 * CG, Cfg::BN) : make_idesc_bf16_f32(128 * CG, Cfg::BN);
       uint32_t stage = 0, phase = 0, it = 0;
-      for (int u = cluster; u < num_units; u += nclusters) {
-        const int s = u / shp.num_m_tiles;
-        const int t0 = s * shp.tiles_per_split;
-        const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
-        for (int t = t0; t < t1; ++t, ++it) {
-          const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
-          mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, kTagMmaTmemEmpty, acc);
+      auto mma_tile = [&]() {
+        const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+        ++it;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, kTagMmaTmemEmpty, acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase, kTagMmaFull, stage);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * Cfg::BN;
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&full_bar[stage], phase, kTagMmaFull, stage);
-            tc_fence_after();
-            const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::A_BYTES));
-            const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::B_BYTES));
-            if (!(shp.debug_flags & 4)) {
+          const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::A_BYTES));
+          const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::B_BYTES));
+          if (!(shp.debug_flags & 4)) {
 #pragma unroll
-              for (int k = 0; k < Cfg::BK / 16; ++k) {
-                // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: start address field += 2
-                umma_bf16<CG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              }
+            for (int k = 0; k < Cfg::BK / 16; ++k) {
+              // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: start address field += 2
+              umma_bf16<CG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit<CG>(&empty_bar[stage]);                       // smem slot free once these MMAs retire
-            if (kb == nkb - 1) umma_commit<CG>(&tmem_full_bar[acc]);  // accumulator complete
-            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
           }
+          umma_commit<CG>(&empty_bar[stage]);                       // smem slot free once these MMAs retire
+          if (kb == nkb - 1) umma_commit<CG>(&tmem_full_bar[acc]);  // accumulator complete
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      };
+      if (shp.skip_below_diagonal) {
+        for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters); w.valid(); w.next()) mma_tile();
+      } else {
+        for (int u = cluster; u < num_units; u += nclusters) {
+          const int s = u / shp.num_m_tiles;
+          const int t0 = s * shp.tiles_per_split;
+          const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
+          for (int t = t0; t < t1; ++t) mma_tile();
         }
       }
     }
@@ -216,38 +250,50 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if constexpr (Epi::kUsesScratch)  // a private staging area per epilogue warp, behind the barriers
       epi.scratch = smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + (warp - 4) * Cfg::EPI_SCRATCH_PER_WARP;
     uint32_t it = 0;
-    for (int u = cluster; u < num_units; u += nclusters) {
-      const int m = u % shp.num_m_tiles, s = u / shp.num_m_tiles;
-      const int t0 = s * shp.tiles_per_split;
-      const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
-      const int row = (m * CG + static_cast<int>(cta_rank)) * Cfg::BM + row_in_tile;
-      epi.begin_unit(ep, row, m, s);
-      for (int t = t0; t < t1; ++t, ++it) {
-        const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
-        mbar_wait(&tmem_full_bar[acc], acc_phase, kTagEpiTmemFull, acc);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::BN +
-                               group * (Cfg::CHUNKS_PER_GROUP * 32);
+    auto epi_tile = [&](int row, int t) {
+      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+      ++it;
+      mbar_wait(&tmem_full_bar[acc], acc_phase, kTagEpiTmemFull, acc);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::BN +
+                             group * (Cfg::CHUNKS_PER_GROUP * 32);
 #pragma unroll 1
-        for (int c = 0; c < Cfg::CHUNKS_PER_GROUP; ++c) {
-          uint32_t v[32];
-          __syncwarp();  // the functor (and the barrier wait) may leave lanes diverged; tcgen05.ld is .sync.aligned
-          if (!(shp.debug_flags & 2)) {
-            tmem_ld_32x32b_x32(taddr + c * 32, v);  // includes tcgen05.wait::ld
-          } else {
+      for (int c = 0; c < Cfg::CHUNKS_PER_GROUP; ++c) {
+        uint32_t v[32];
+        __syncwarp();  // the functor (and the barrier wait) may leave lanes diverged; tcgen05.ld is .sync.aligned
+        if (!(shp.debug_flags & 2)) {
+          tmem_ld_32x32b_x32(taddr + c * 32, v);  // includes tcgen05.wait::ld
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0u;
-          }
-          if (c == Cfg::CHUNKS_PER_GROUP - 1) {
-            // this thread's share of the accumulator stage is in registers: hand it back to the MMA warp
-            tc_fence_before();
-            if (CG == 1 || leader) mbar_arrive(&tmem_empty_bar[acc]);
-            else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
-          }
-          if (!(shp.debug_flags & 1)) epi.chunk(ep, row, t * Cfg::BN + (group * Cfg::CHUNKS_PER_GROUP + c) * 32, v);
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
+        if (c == Cfg::CHUNKS_PER_GROUP - 1) {
+          // this thread's share of the accumulator stage is in registers: hand it back to the MMA warp
+          tc_fence_before();
+          if (CG == 1 || leader) mbar_arrive(&tmem_empty_bar[acc]);
+          else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        }
+        if (!(shp.debug_flags & 1)) epi.chunk(ep, row, t * Cfg::BN + (group * Cfg::CHUNKS_PER_GROUP + c) * 32, v);
       }
-      epi.end_unit(ep, row, m, s * Cfg::EPI_GROUPS + group);
+    };
+    if (shp.skip_below_diagonal) {
+      // every tile is its own unit (the functors used with this schedule keep no state across tiles)
+      for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters); w.valid(); w.next()) {
+        const int row = (w.m * CG + static_cast<int>(cta_rank)) * Cfg::BM + row_in_tile;
+        epi.begin_unit(ep, row, w.m, w.t);
+        epi_tile(row, w.t);
+        epi.end_unit(ep, row, w.m, w.t * Cfg::EPI_GROUPS + group);
+      }
+    } else {
+      for (int u = cluster; u < num_units; u += nclusters) {
+        const int m = u % shp.num_m_tiles, s = u / shp.num_m_tiles;
+        const int t0 = s * shp.tiles_per_split;
+        const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
+        const int row = (m * CG + static_cast<int>(cta_rank)) * Cfg::BM + row_in_tile;
+        epi.begin_unit(ep, row, m, s);
+        for (int t = t0; t < t1; ++t) epi_tile(row, t);
+        epi.end_unit(ep, row, m, s * Cfg::EPI_GROUPS + group);
+      }
     }
   }
 

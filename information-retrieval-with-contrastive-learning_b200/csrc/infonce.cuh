@@ -136,6 +136,8 @@ struct GradLogitEpilogue {
     float scale_log2;
     float coef;
     int debug = 0;           // tuning instrumentation (debug.flags): 8 skip the stores
+    int mirror_rows = 0;     // mode 0, H symmetric: rows per A tile (256) when the tiles below the diagonal block are
+                             // not computed (GemmShape::skip_below_diagonal): a chunk above it is also written transposed
   };
   static constexpr bool kUsesScratch = sizeof(OutT) == 2;
   uint8_t* scratch = nullptr;  // per-warp smem staging (tensor-core kernel only), see store32_coalesced
@@ -197,7 +199,31 @@ struct GradLogitEpilogue {
       if (row0 + r < p.rows_a)
         *reinterpret_cast<uint4*>(p.out + static_cast<long long>(row0 + r) * p.ld_out + col0 + 8 * piece) = val;
     }
-    __syncwarp();  // the staging area is reused by the next chunk
+    __syncwarp();  // the staging area is reused by the next chunk (store32_mirrored, if any, only reads it)
+  }
+
+  // The transposed copy of the chunk store32_coalesced has just staged (H is symmetric): element (r, j) of the
+  // 32 x 32 block goes to out[col0 + j][row0 + r].  Four lanes cover an output row's 64 bytes, as above.
+  __device__ __forceinline__ void store32_mirrored(const Params& p, int row, int col0) const {
+    const int lane = threadIdx.x & 31;
+    constexpr int kPitch = 80;
+    const int row0 = row - lane, piece = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = (lane >> 2) + 8 * i;  // column of the block = output row
+      uint32_t w[4];
+#pragma unroll
+      for (int h2 = 0; h2 < 4; ++h2) {
+        const int r = 8 * piece + 2 * h2;
+        const uint32_t lo = *reinterpret_cast<const unsigned short*>(scratch + r * kPitch + 2 * j);
+        const uint32_t hi = *reinterpret_cast<const unsigned short*>(scratch + (r + 1) * kPitch + 2 * j);
+        w[h2] = lo | (hi << 16);
+      }
+      // (the host enables mirroring only when the rows are a multiple of the tile: every chunk is full)
+      *reinterpret_cast<uint4*>(p.out + static_cast<long long>(col0 + j) * p.ld_out + row0 + 8 * piece) =
+            make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __syncwarp();
   }
 
   __device__ __forceinline__ void chunk(const Params& p, int row, int col0, const uint32_t (&v)[32]) {
@@ -247,6 +273,9 @@ struct GradLogitEpilogue {
         if constexpr (kUsesScratch) {
           if (staged) {
             store32_coalesced(p, row, col0, h);
+            // (row - lane) / mirror_rows is the A tile of the whole warp: the condition is warp-uniform
+            if (p.mirror_rows > 0 && col0 >= ((row - (threadIdx.x & 31)) / p.mirror_rows + 1) * p.mirror_rows)
+              store32_mirrored(p, row, col0);
             return;
           }
         }
@@ -311,6 +340,12 @@ struct GradLogitEpilogue {
         for (int j = 0; j < 32; ++j)
           if (j < valid) dst[j] = h[j];
       }
+    }
+    // the rare chunk that holds a positive, above the diagonal block: its mirror image is not computed either
+    if (p.mirror_rows > 0 && col0 >= (row / p.mirror_rows + 1) * p.mirror_rows) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < valid) p.out[static_cast<long long>(col0 + j) * p.ld_out + row] = static_cast<OutT>(h[j]);
     }
   }
   __device__ __forceinline__ void end_unit(const Params&, int, int, int) {}

@@ -177,3 +177,24 @@ def test_nceloss_with_cluster_result_adds_proto_loss():
     assert abs(loss.item() - ref) <= 1e-5 * abs(ref)
     rdq = dq_info + dq_proto
     assert (qd.grad.cpu().double() - rdq).abs().max().item() <= 1e-4 * rdq.abs().max().item()
+
+
+def test_symmetric_gradient_matrix_matches_the_full_computation():
+    """Backward at whole 256-row tiles computes only the blocks of H = dL/dS on and above the diagonal and writes
+    each twice (itself and its transpose); the gradients must equal the full computation and the oracle."""
+    n, dim = 1024, 128
+    g = torch.Generator().manual_seed(5)
+    q = torch.nn.functional.normalize(torch.randn(n, dim, generator=g), dim=1)
+    k = torch.nn.functional.normalize(torch.randn(n, dim, generator=g) * 0.5 + q, dim=1)
+    loss1, dq1, dk1 = _run(q, k, None, 0.05, "bf16")
+    try:
+        drs_b200.set_option("tune.symmetric_grad", 0)
+        loss0, dq0, dk0 = _run(q, k, None, 0.05, "bf16")
+    finally:
+        drs_b200.set_option("tune.symmetric_grad", 1)
+    assert loss1.item() == loss0.item()
+    scale = dq0.abs().max().item()
+    assert (dq1 - dq0).abs().max().item() <= 1e-6 * scale and (dk1 - dk0).abs().max().item() <= 1e-6 * scale
+    rl, rdq, rdk = infonce.nce_info_loss(q, k, None, 0.05, dtype=torch.float64)
+    assert (dq1.double() - rdq).abs().max().item() <= 3e-2 * rdq.abs().max().item()
+    assert (dk1.double() - rdk).abs().max().item() <= 3e-2 * rdk.abs().max().item()
