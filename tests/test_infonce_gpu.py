@@ -198,3 +198,37 @@ def test_symmetric_gradient_matrix_matches_the_full_computation():
     rl, rdq, rdk = infonce.nce_info_loss(q, k, None, 0.05, dtype=torch.float64)
     assert (dq1.double() - rdq).abs().max().item() <= 3e-2 * rdq.abs().max().item()
     assert (dk1.double() - rdk).abs().max().item() <= 3e-2 * rdk.abs().max().item()
+
+
+def test_loss_step_is_cuda_graph_capturable():
+    """Forward + backward of NCELoss captured once in a CUDA graph and replayed on new embeddings: same loss and
+    gradients as the eager call (a trainer can take the ~20 small launches off the host)."""
+    n, dim = 512, 128
+    g = torch.Generator(device=DEV).manual_seed(11)
+    q = torch.nn.functional.normalize(torch.randn(n, dim, generator=g, device=DEV), dim=1).requires_grad_(True)
+    k = torch.nn.functional.normalize(torch.randn(n, dim, generator=g, device=DEV), dim=1).requires_grad_(True)
+    crit = drs_b200.NCELoss({"temperature": 0.05})
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            q.grad = k.grad = None
+            crit(q, k, None).backward()
+    torch.cuda.current_stream().wait_stream(side)
+    q.grad = k.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss = crit(q, k, None)
+        loss.backward()
+    for seed in (1, 2):
+        gg = torch.Generator(device=DEV).manual_seed(seed)
+        with torch.no_grad():
+            q.copy_(torch.nn.functional.normalize(torch.randn(n, dim, generator=gg, device=DEV), dim=1))
+            k.copy_(torch.nn.functional.normalize(torch.randn(n, dim, generator=gg, device=DEV) * 0.3 + q, dim=1))
+        graph.replay()
+        torch.cuda.synchronize()
+        got = (loss.item(), q.grad.clone(), k.grad.clone())
+        q2, k2 = q.detach().clone().requires_grad_(True), k.detach().clone().requires_grad_(True)
+        l2 = crit(q2, k2, None)
+        l2.backward()
+        assert got[0] == l2.item() and torch.equal(got[1], q2.grad) and torch.equal(got[2], k2.grad)
