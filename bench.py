@@ -380,6 +380,10 @@ def run_b200(args):
     #      corpus pass, intensity = B flop/byte, HBM-bound below the ridge (~212).  Same corpus, same call.
     regimes = []
     if not args.no_extras:
+        # the timed loops above ran the chip at its power cap for several seconds; let the clocks recover so that
+        # these millisecond-scale measurements do not inherit the throttled state (they are reported separately)
+        barrier()
+        time.sleep(2.0)
         for bq in (1, 16, 64, 128, 256):
             qs = queries[:bq].contiguous()
             rprof = []

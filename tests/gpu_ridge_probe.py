@@ -30,7 +30,7 @@ def main():
         c[r0:r1] = torch.nn.functional.normalize(torch.randn(r1 - r0, 768, generator=g, device=dev), dim=1)
     qa = torch.nn.functional.normalize(torch.randn(1024, 768, generator=g, device=dev), dim=1).bfloat16()
     t_hbm = nc * 768 * 2 / 6.551e12 * 1e3
-    for nq in (192, 256, 384, 512):
+    for nq in (64, 128, 192, 256):
         q = qa[:nq].contiguous()
         t_mma = 2.0 * nq * nc * 768 / 1389.5e12 * 1e3
         line = f"nq={nq:5d} roof {max(t_hbm, t_mma):6.3f} ms |"
