@@ -94,6 +94,29 @@ def docs_sentence_pairs(doc_matrices: Sequence, device=None):
     return [[((pi[t], pj[t]), ps[t]) for t in range(int(off[d]), int(off[d + 1]))] for d in range(len(off) - 1)]
 
 
+def _reference_vectorizer():
+    """The vectoriser the reference builds at build_docs_sentence_similarity.py:43: word-level TF-IDF over uni- and
+    bigrams whose tokenizer (:27-38) drops punctuation marks and English stop words (nltk corpus, :17-22) and
+    lemmatises what is left with WordNet.  Needs nltk and its data, exactly like the reference."""
+    import string
+    from sklearn.feature_extraction.text import TfidfVectorizer
+    try:
+        from nltk import word_tokenize
+        from nltk.corpus import stopwords as nltk_stopwords
+        from nltk.stem import WordNetLemmatizer
+        stop = set(nltk_stopwords.words("english"))
+    except (ImportError, LookupError) as e:  # the reference imports nltk and downloads its corpora at module scope
+        raise RuntimeError("the reference's LemmaTokenizer needs nltk with the wordnet, stopwords and punkt data; "
+                           "pass vectorizer=... instead") from e
+    lemmatizer = WordNetLemmatizer()
+
+    def lemma_tokens(sentence):
+        kept = [tok for tok in word_tokenize(sentence) if tok not in string.punctuation and tok not in stop]
+        return [lemmatizer.lemmatize(tok) for tok in kept]
+
+    return TfidfVectorizer(tokenizer=lemma_tokens, ngram_range=(1, 2))
+
+
 def get_docs_sents_similarity(full_data, small_data, vectorizer=None, device=None):
     """Drop-in for build_docs_sentence_similarity.py:41-68.
 
@@ -102,23 +125,7 @@ def get_docs_sents_similarity(full_data, small_data, vectorizer=None, device=Non
     ngram_range=(1, 2))`` (:43), which needs nltk -- pass your own when nltk is not installed.  It is
     fitted on every sentence of ``full_data`` (:44-45) unless it already has a vocabulary."""
     if vectorizer is None:
-        from sklearn.feature_extraction.text import TfidfVectorizer
-        try:
-            from nltk import word_tokenize
-            from nltk.stem import WordNetLemmatizer
-        except ImportError as e:  # the reference imports nltk at module scope (:9-12)
-            raise RuntimeError("the reference's LemmaTokenizer needs nltk; pass vectorizer=... instead") from e
-
-        class LemmaTokenizer:   # :27-38
-            ignore_tokens = [",", ".", ";", ":", '"', "``", "''", "`"]
-
-            def __init__(self):
-                self.wnl = WordNetLemmatizer()
-
-            def __call__(self, doc):
-                return [self.wnl.lemmatize(t) for t in word_tokenize(doc) if t not in self.ignore_tokens]
-
-        vectorizer = TfidfVectorizer(tokenizer=LemmaTokenizer(), ngram_range=(1, 2))
+        vectorizer = _reference_vectorizer()
     if not hasattr(vectorizer, "vocabulary_"):
         vectorizer.fit([sent for doc in full_data for sent in doc])
     mats = [vectorizer.transform(doc) for doc in small_data]

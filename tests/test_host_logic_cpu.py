@@ -129,3 +129,13 @@ def test_pair_builder_host_logic_and_no_cpu_path():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             drs_b200.docs_sentence_pairs([np.eye(3)])
+
+
+def test_default_vectoriser_is_the_references_and_says_so_when_nltk_is_missing():
+    """build_docs_sentence_similarity.py:27-43: the default vectoriser needs nltk (WordNet lemmas, English stop
+    words); where nltk is absent the builder must say so instead of substituting another tokenizer."""
+    try:
+        import nltk  # noqa: F401
+    except ImportError:
+        with pytest.raises(RuntimeError, match="vectorizer"):
+            drs_b200.get_docs_sents_similarity([["a b"]], [["a b"]])
