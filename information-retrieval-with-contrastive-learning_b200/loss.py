@@ -257,7 +257,6 @@ class NCELoss(torch.nn.Module):
         if 'cluster' in loss_config:                              # :52-54
             self.num_cluster = loss_config['cluster']['num_cluster']
             self.num_neg_proto = loss_config['cluster']['num_neg_proto']
-        self._rng = random.Random(1126)                           # the reference seeds `random` with 1126 (:4)
 
     def _compute_info_loss(self, q, k, queue=None):
         return info_nce_loss(q, k, queue, self.T, self.precision)
@@ -266,7 +265,9 @@ class NCELoss(torch.nn.Module):
         """The host-side selection of contrastive_loss.py:99-112,:122-123: positive prototype of
         each sample, ``num_neg_proto`` sampled negatives, and their densities.
         ``random.sample(set, r)`` (:109) raises on Python >= 3.11, so the population is sorted
-        first (a set has no defined order anyway); everything else follows the reference,
+        first (a set has no defined order anyway); the draw comes from the global ``random`` stream like
+        upstream's ``from random import sample``, so ``random.seed(args.seed)`` (main.py:95) governs it;
+        everything else follows the reference,
         including ``range(emb2cluster.max())`` (:105), which leaves the highest cluster id out."""
         protos, temps = [], []
         for emb2cluster, prototypes, density in zip(cluster_result['emb2cluster'], cluster_result['centroids'],
@@ -274,7 +275,7 @@ class NCELoss(torch.nn.Module):
             pos_proto_id = emb2cluster[index.tolist()]                                   # :101
             all_proto_id = range(int(emb2cluster.max()))                                 # :105
             neg_proto_id = sorted(set(all_proto_id) - set(pos_proto_id.tolist()))        # :106
-            neg_proto_id = self._rng.sample(neg_proto_id, self.num_neg_proto)            # :109
+            neg_proto_id = random.sample(neg_proto_id, self.num_neg_proto)               # :109 (the global RNG, as upstream)
             ids = torch.cat([pos_proto_id.cpu().long(), torch.LongTensor(neg_proto_id)])
             protos.append(prototypes[ids.to(prototypes.device)])                         # :102,:110,:112
             temps.append(density[ids.to(density.device)])                                # :122-123
