@@ -166,9 +166,12 @@ def test_nceloss_with_cluster_result_adds_proto_loss():
     cfg = {"temperature": 0.05, "precision": "fp32", "cluster": {"num_cluster": ncl, "num_neg_proto": r}}
     crit = drs_b200.NCELoss(cfg)
     qd = q.to(DEV).requires_grad_(True)
+    import random
+    random.seed(1126)                                              # the negatives come from the global stream (:4,:109)
     loss = crit(qd, k.to(DEV), None, cluster_result=cr, index=index)
     loss.backward()
-    twin = drs_b200.NCELoss(cfg)                                   # same seed -> same selection
+    twin = drs_b200.NCELoss(cfg)
+    random.seed(1126)                                              # same seed -> same selection
     protos, temps = twin.select_prototypes(cr, index)
     assert all(p.shape == (n + r, dim) for p in protos)
     l_info, dq_info, _ = infonce.nce_info_loss(q, k, None, 0.05, dtype=torch.float64)
