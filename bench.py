@@ -344,6 +344,36 @@ def run_b200(args):
             ms = t.item()
         return ms
 
+    # ---- the small-query-batch, bandwidth-bound regime (SURVEY.md 8d rows 2b/3b): B claims share one
+    #      corpus pass, intensity = B flop/byte, HBM-bound below the ridge (~212).  Same corpus, same call.
+    regimes = []
+    if not args.no_extras:
+        # measured BEFORE the headline loops: those run the chip at its power cap for seconds, and millisecond-scale
+        # measurements taken right after them inherit the throttled clocks (reported separately from `value`)
+        for bq in (1, 16, 64, 128, 256):
+            qs = queries[:bq].contiguous()
+            rprof = []
+            for _ in range(3):
+                index.search(qs, k)
+            reps = 10
+            ms = timed_loop(lambda: index.search(qs, k, profile=rprof), reps) / reps
+            kms = sum(a.elapsed_time(b) for a, b in rprof) / max(1, len(rprof))
+            if world > 1:
+                t = torch.tensor([kms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                kms = t.item()
+            rows_r = hi - lo
+            byt = rows_r * dim * 2 + bq * dim * 2 + bq * k * 12
+            flp = 2.0 * bq * rows_r * dim
+            gbs = byt / (kms * 1e-3) / 1e9
+            tfl = flp / (kms * 1e-3) / 1e12
+            t_hbm, t_mma = byt / (peaks["hbm_gbs"] * 1e9), flp / (peaks["tflops"] * 1e12)
+            regimes.append({"claims_per_pass": bq, "ms_per_step": ms, "scan_kernel_ms": kms,
+                            "claims_per_s": bq / (ms * 1e-3), "hbm_gbs_per_gpu": gbs,
+                            "hbm_frac": gbs / peaks["hbm_gbs"], "mma_frac": tfl / peaks["tflops"],
+                            "bound": "hbm" if t_hbm >= t_mma else "tensor",
+                            "roofline_frac": max(t_hbm, t_mma) / (kms * 1e-3)})
+
     # ---- device-resident throughput (`value`) with the scan kernel bracketed by events (roofline)
     prof = []
 
@@ -375,38 +405,6 @@ def run_b200(args):
     e2e = {"value": nq / (e2e_ms * 1e-3), "unit": "claims/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": queries_host.numel() * queries_host.element_size(),
            "d2h_bytes_per_step": out_s.numel() * 4 + out_i.numel() * 8}
-
-    # ---- the small-query-batch, bandwidth-bound regime (SURVEY.md 8d rows 2b/3b): B claims share one
-    #      corpus pass, intensity = B flop/byte, HBM-bound below the ridge (~212).  Same corpus, same call.
-    regimes = []
-    if not args.no_extras:
-        # the timed loops above ran the chip at its power cap for several seconds; let the clocks recover so that
-        # these millisecond-scale measurements do not inherit the throttled state (they are reported separately)
-        barrier()
-        time.sleep(2.0)
-        for bq in (1, 16, 64, 128, 256):
-            qs = queries[:bq].contiguous()
-            rprof = []
-            for _ in range(3):
-                index.search(qs, k)
-            reps = 10
-            ms = timed_loop(lambda: index.search(qs, k, profile=rprof), reps) / reps
-            kms = sum(a.elapsed_time(b) for a, b in rprof) / max(1, len(rprof))
-            if world > 1:
-                t = torch.tensor([kms], device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                kms = t.item()
-            rows_r = hi - lo
-            byt = rows_r * dim * 2 + bq * dim * 2 + bq * k * 12
-            flp = 2.0 * bq * rows_r * dim
-            gbs = byt / (kms * 1e-3) / 1e9
-            tfl = flp / (kms * 1e-3) / 1e12
-            t_hbm, t_mma = byt / (peaks["hbm_gbs"] * 1e9), flp / (peaks["tflops"] * 1e12)
-            regimes.append({"claims_per_pass": bq, "ms_per_step": ms, "scan_kernel_ms": kms,
-                            "claims_per_s": bq / (ms * 1e-3), "hbm_gbs_per_gpu": gbs,
-                            "hbm_frac": gbs / peaks["hbm_gbs"], "mma_frac": tfl / peaks["tflops"],
-                            "bound": "hbm" if t_hbm >= t_mma else "tensor",
-                            "roofline_frac": max(t_hbm, t_mma) / (kms * 1e-3)})
 
     # ---- BASELINE configs[3]: in-batch InfoNCE, batch 4096 x 768, fused logits + softmax-CE fwd/bwd
     infonce_line = other_configs = None
