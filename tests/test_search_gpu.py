@@ -454,3 +454,21 @@ def test_fp16_operands_on_the_tensor_core_path(nq, nc, dim, k):
                                rtol=1e-4, atol=1e-5)
     idx = drs_b200.DenseIndex(c, dtype=torch.float16)
     assert idx.embeddings.dtype == torch.float16 and torch.equal(idx.search(q, k)[1], i)
+
+
+def test_many_claims_and_rerank_extremes():
+    """More claims than one grid of A tiles can hold at once (70 000 -> 274 pair tiles, seeded thresholds, ragged
+    last tile) against the oracle on a sample; re-rank with a single candidate and with 3000 candidates."""
+    nq, nc, dim, k = 70_000, 20_000, 64, 10
+    q, c = _data(nq, nc, dim, torch.bfloat16, planted=True)
+    s, i = drs_b200.search(q, c, k)
+    pick = torch.randint(0, nq, (200,), generator=torch.Generator().manual_seed(0))
+    pick[0], pick[1] = 0, nq - 1
+    _check(q[pick.to(DEV)], c, k, s[pick.to(DEV)], i[pick.to(DEV)], score_rtol=2e-2, gap=1e-4)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    for m, kk in ((1, 1), (3000, 15)):
+        cand = torch.randint(0, nc, (64, m), generator=g, device=DEV)
+        rs, ri = drs_b200.rerank(q[:64], c, cand, kk)
+        os_, oi = dense_topk.rerank(q[:64].cpu(), c.cpu(), cand.cpu(), kk)
+        torch.testing.assert_close(rs.cpu(), os_, rtol=1e-4, atol=1e-5)
+        assert torch.equal(ri.cpu()[:, 0], oi[:, 0])
