@@ -22,6 +22,8 @@ from . import _lib
 
 _DTYPES = {torch.float32: _lib.DRS_F32, torch.bfloat16: _lib.DRS_BF16, torch.float16: _lib.DRS_F16}
 
+MAX_CLAIMS_PER_PASS = 1 << 18   # claims scored per engine call by `search` (larger batches are sliced)
+
 # one cached workspace per (device, stream) so steady-state searches allocate nothing
 _workspaces: dict = {}
 
@@ -79,6 +81,12 @@ def search(queries: torch.Tensor, corpus: torch.Tensor, k: int, *, id_base: int 
         raise RuntimeError(f"k={kk} exceeds the engine limit of {_lib.DRS_MAX_K}")
     queries = queries.contiguous()
     corpus = corpus.contiguous()
+    if nq > MAX_CLAIMS_PER_PASS:
+        # the candidate workspace grows with the claim count (~10 KB per claim): very large batches go through in
+        # slices (the scan is tensor-bound at these sizes, so re-streaming the corpus per slice costs nothing)
+        parts = [search(queries[a:a + MAX_CLAIMS_PER_PASS], corpus, k, id_base=id_base)
+                 for a in range(0, nq, MAX_CLAIMS_PER_PASS)]
+        return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
     lib = _lib.load()
     dt = _DTYPES[corpus.dtype]
     with torch.cuda.device(dev):

@@ -472,3 +472,13 @@ def test_many_claims_and_rerank_extremes():
         os_, oi = dense_topk.rerank(q[:64].cpu(), c.cpu(), cand.cpu(), kk)
         torch.testing.assert_close(rs.cpu(), os_, rtol=1e-4, atol=1e-5)
         assert torch.equal(ri.cpu()[:, 0], oi[:, 0])
+
+
+def test_claim_batches_beyond_the_per_pass_limit_are_sliced(monkeypatch):
+    from importlib import import_module
+    retrieval = import_module(drs_b200.__name__ + ".retrieval")
+    q, c = _data(1000, 5000, 64, torch.bfloat16, planted=True)
+    s0, i0 = drs_b200.search(q, c, 10)
+    monkeypatch.setattr(retrieval, "MAX_CLAIMS_PER_PASS", 300)
+    s1, i1 = drs_b200.search(q, c, 10)
+    assert torch.equal(i0, i1) and torch.equal(s0, s1)
