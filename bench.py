@@ -5,10 +5,18 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU scoring idiom
 
 One step = one pass of the hot path over one batch: 10 000 claim embeddings scored against the
-whole corpus (row-sharded over the N ranks), fused top-10 per shard, all-gather of the per-shard
-lists over NCCL and the on-GPU merge.  The corpus size is fixed at 25M rows as N grows
-("scaling": "strong").  Synthetic data: seeded randn rows, L2-normalised like
-contrastive_module.py:111, generated on the device shard by shard (seed 1337 + rank).
+whole corpus (row-sharded over the N ranks), fused top-10 per shard, then ONE exchange step: the
+fused select + NVLink peer-memory exchange + merge kernel (k <= 16), the query-sliced peer-memory
+exchange (larger k), or -- when peer memory cannot be mapped -- an NCCL all-gather + on-GPU merge.
+The corpus size is fixed at 25M rows as N grows ("scaling": "strong").  Synthetic data: seeded
+randn rows, L2-normalised like contrastive_module.py:111, generated on the device shard by shard
+(seed 1337 + rank); the last 16 claims of the batch are PLANTED (a corpus row + 0.05 x noise).
+
+After the timed loops (outside them) the results the timed steps produced are verified: a 64-claim
+sample is scored by brute force (fp32 torch.matmul per shard + a stable (score desc, id asc) select,
+all-gathered over the ranks) and compared with what the engine returned -- ids exact wherever the
+score gap exceeds 1e-4, scores within 2e-2 -- and every planted claim must come back with its row
+first.  The verdict is the "parity" object of the JSON line.
 
 Output: ONE JSON line on rank 0 (see the README / DESIGN.md for the keys).
 """
@@ -135,11 +143,14 @@ def cpu_reference_rate(nq, nc, dim, k, target_seconds, steps=1, warmup=0):
     dense_topk.search_fast(q, c, k)
     probe = time.perf_counter() - t0
     flops_per_s = 2.0 * pq * pr * dim / probe
-    sq = 256
+    # The reference holds fp32 embeddings (ctx2vec output, contrastive_module.py:96-112), so the sample corpus is
+    # upcast ONCE, outside the timed loop, and 1024 claims share every pass over it (a 256-claim sample that
+    # re-upcasts each bf16 chunk inside the loop charges the CPU arm a cost the full 10 000-claim pass amortises).
+    sq = 1024
     sr = int(min(nc, max(pr, target_seconds * flops_per_s / (2.0 * sq * dim))))
-    sr = max(pr, min(sr, 4_000_000))        # bound host memory (bf16 rows + fp32 chunk copies)
-    c = torch.nn.functional.normalize(torch.randn(sr, dim, generator=g), dim=1).bfloat16()
-    q = torch.nn.functional.normalize(torch.randn(sq, dim, generator=g), dim=1).bfloat16()
+    sr = max(pr, min(sr, 2_000_000))        # bound host memory: fp32 rows (6 GB at 2M x 768)
+    c = torch.nn.functional.normalize(torch.randn(sr, dim, generator=g), dim=1).bfloat16().float()
+    q = torch.nn.functional.normalize(torch.randn(sq, dim, generator=g), dim=1).bfloat16().float()
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -149,8 +160,9 @@ def cpu_reference_rate(nq, nc, dim, k, target_seconds, steps=1, warmup=0):
     t = sum(times) / len(times)
     rate_full = sq / (t * (nc / sr))
     return dict(value=rate_full, unit="claims/s", cores=threads, kind="port",
-                sample=f"{sq} claims x {sr} rows x {dim} bf16 (upcast to fp32, torch.matmul + topk, {threads} threads), "
-                       f"{t:.2f} s/step; claims/s extrapolated linearly to {nc} rows"), t
+                sample=f"{sq} claims x {sr} rows x {dim} (the bf16 values, upcast to fp32 once outside the timed loop; "
+                       f"fp32 torch.matmul + topk, {threads} threads), {t:.2f} s/step; claims/s extrapolated linearly "
+                       f"to {nc} rows"), t
 
 
 def run_reference(args):
@@ -289,7 +301,87 @@ def bench_infonce(torch, drs_b200, dev, peaks, n=4096, dim=768, temperature=0.05
             "ms_per_step": ms, "cuda_graph_replay_ms_per_step": graph_ms, "steps_per_s": 1e3 / ms,
             "tflops": flops / (ms * 1e-3) / 1e12,
             "mma_frac": flops / (ms * 1e-3) / 1e12 / peaks["tflops"],
-            "logit_matrix_bytes_never_materialised": 4 * (2 * n) ** 2}
+            "forward_logit_bytes_not_materialised": 4 * (2 * n) ** 2,
+            "backward_workspace_bytes": _infonce_workspace_bytes(n, dim)}
+
+
+def _infonce_workspace_bytes(n, dim):
+    """what drs_infonce_workspace_bytes reports for the bf16 step (operand copies, LSE partials and the
+    gradient-of-logits workspace of the backward), so the line says what IS materialised"""
+    import ctypes
+    from drs_b200 import _lib
+    need = ctypes.c_size_t(0)
+    _lib.check(_lib.load().drs_infonce_workspace_bytes(n, dim, 0, _lib.DRS_BF16, ctypes.byref(need)))
+    return need.value
+
+
+def brute_force_topk(torch, q, shard, id_base, kk, chunk_rows=1 << 20):
+    """Checker (not timed, not the product): fp32 torch.matmul of the sampled claims against this rank's rows
+    (the bf16 values upcast -- the scoring idiom of contrastive_loss.py:62), running (score desc, id asc) top-kk."""
+    qf = q.float()
+    best_s = torch.empty(q.shape[0], 0, dtype=torch.float32, device=q.device)
+    best_i = torch.empty(q.shape[0], 0, dtype=torch.int64, device=q.device)
+    for r0 in range(0, shard.shape[0], chunk_rows):
+        blk = shard[r0:r0 + chunk_rows].float()
+        sc = qf @ blk.T
+        s, i = torch.topk(sc, min(kk + 8, sc.shape[1]), dim=1)      # a margin so that ties at the cut are all present
+        best_s, best_i = merge_sorted(torch, torch.cat([best_s, s], 1), torch.cat([best_i, i + (id_base + r0)], 1), kk + 8)
+        del blk, sc
+    return best_s, best_i
+
+
+def merge_sorted(torch, s, i, kk):
+    """rows of (score, id) candidates -> the kk best by (score desc, id asc)"""
+    o = torch.argsort(i, dim=1, stable=True)
+    s, i = torch.gather(s, 1, o), torch.gather(i, 1, o)
+    o = torch.argsort(s, dim=1, descending=True, stable=True)
+    s, i = torch.gather(s, 1, o), torch.gather(i, 1, o)
+    return s[:, :kk].contiguous(), i[:, :kk].contiguous()
+
+
+def parity_check(torch, dist, world, dev, shard, lo, queries, k, got_s, got_i, planted_claims, planted_rows, sample=64):
+    """Verify the results of the timed steps (see the module docstring).  Runs on every rank; returns a dict."""
+    nq = queries.shape[0]
+    n_pl = len(planted_claims)
+    reg = torch.linspace(0, nq - n_pl - 1, max(1, sample - n_pl)).long().unique()
+    pick = torch.cat([reg, torch.tensor(planted_claims, dtype=torch.int64)]).to(dev)
+    ref_s, ref_i = brute_force_topk(torch, queries[pick], shard, lo, k + 1)
+    if world > 1:
+        all_s = [torch.empty_like(ref_s) for _ in range(world)]
+        all_i = [torch.empty_like(ref_i) for _ in range(world)]
+        dist.all_gather(all_s, ref_s)
+        dist.all_gather(all_i, ref_i)
+        ref_s, ref_i = merge_sorted(torch, torch.cat(all_s, 1), torch.cat(all_i, 1), k + 1)
+    ref_s, ref_i = ref_s[:, :k + 1].cpu(), ref_i[:, :k + 1].cpu()
+    gs, gi = got_s[pick].cpu(), got_i[pick].cpu()
+    gap_tol, compared, mismatched, max_rel = 1e-4, 0, 0, 0.0
+    for r in range(gs.shape[0]):
+        for j in range(k):
+            rs = ref_s[r, j].item()
+            max_rel = max(max_rel, abs(gs[r, j].item() - rs) / max(abs(rs), 1e-6))
+            above = ref_s[r, j - 1].item() - rs if j else float("inf")
+            below = rs - ref_s[r, j + 1].item() if j + 1 < ref_s.shape[1] else float("inf")
+            if above > gap_tol and below > gap_tol:          # this rank's occupant is unambiguous
+                compared += 1
+                mismatched += int(gi[r, j].item() != ref_i[r, j].item())
+    planted_ok = all(int(got_i[c, 0].item()) == int(row) for c, row in zip(planted_claims, planted_rows))
+    desc = bool((got_s[:, :-1] >= got_s[:, 1:]).all().item()) if k > 1 else True
+    agree = True
+    if world > 1:                                             # every rank holds the same answer
+        chk = torch.stack([got_i.sum().double(), got_s.double().sum()])
+        lo_, hi_ = chk.clone(), chk.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        agree = bool(torch.equal(lo_, hi_))
+    ok = mismatched == 0 and max_rel <= 2e-2 and planted_ok and desc and agree
+    if world > 1:
+        flag = torch.tensor([int(ok)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item())
+    return {"checked": int(gs.shape[0]), "planted": n_pl, "ok": bool(ok), "ids_compared": compared, "ids_mismatched": mismatched,
+            "max_rel_err": max_rel, "planted_top1_ok": bool(planted_ok), "sorted_desc": desc, "ranks_agree": agree,
+            "method": "results of the last timed step vs fp32 torch.matmul per shard + stable (score desc, id asc) select, "
+                      "all-gathered over the ranks; ids exact where the reference's score gap > 1e-4, scores within 2e-2"}
 
 
 # --------------------------------------------------------------------------------- B200 arm
@@ -321,6 +413,19 @@ def run_b200(args):
         shard[r0:r1] = torch.nn.functional.normalize(torch.randn(r1 - r0, dim, generator=g, device=dev), dim=1)
     gq = torch.Generator(device=dev).manual_seed(4242)      # same claims on every rank
     queries = torch.nn.functional.normalize(torch.randn(nq, dim, generator=gq, device=dev), dim=1).bfloat16()
+    # planted claims (the last 16 of the batch): corpus row + 0.05 x noise, rows spread over the whole corpus.  The
+    # owning rank contributes the row, an all-reduce hands it to everyone, the noise is the same on every rank.
+    n_pl = min(16, nq // 2)
+    planted_rows = [((2 * p + 1) * nc) // (2 * n_pl) for p in range(n_pl)]
+    planted_claims = list(range(nq - n_pl, nq))
+    rows_f = torch.zeros(n_pl, dim, dtype=torch.float32, device=dev)
+    for p, row in enumerate(planted_rows):
+        if lo <= row < hi:
+            rows_f[p] = shard[row - lo].float()
+    if world > 1:
+        dist.all_reduce(rows_f)
+    noise = torch.randn(n_pl, dim, generator=torch.Generator(device=dev).manual_seed(777), device=dev)
+    queries[nq - n_pl:] = torch.nn.functional.normalize(rows_f + 0.05 * noise, dim=1).bfloat16()
     queries_host = queries.cpu().pin_memory()
     index = drs_b200.ShardedDenseIndex(shard, nc, device=dev) if world > 1 else drs_b200.DenseIndex(shard, device=dev)
 
@@ -350,12 +455,12 @@ def run_b200(args):
     if not args.no_extras:
         # measured BEFORE the headline loops: those run the chip at its power cap for seconds, and millisecond-scale
         # measurements taken right after them inherit the throttled clocks (reported separately from `value`)
-        for bq in (1, 16, 64, 128, 256):
+        for bq in (1, 16, 64, 128, 256, 384, 512, 1024, 2048):
             qs = queries[:bq].contiguous()
             rprof = []
             for _ in range(3):
                 index.search(qs, k)
-            reps = 10
+            reps = 10 if bq <= 256 else 5
             ms = timed_loop(lambda: index.search(qs, k, profile=rprof), reps) / reps
             kms = sum(a.elapsed_time(b) for a, b in rprof) / max(1, len(rprof))
             if world > 1:
@@ -377,8 +482,10 @@ def run_b200(args):
     # ---- device-resident throughput (`value`) with the scan kernel bracketed by events (roofline)
     prof = []
 
+    last = {}
+
     def step_resident():
-        return index.search(queries, k, profile=prof)
+        last["s"], last["i"] = index.search(queries, k, profile=prof)
 
     for _ in range(args.warmup):
         step_resident()
@@ -405,6 +512,12 @@ def run_b200(args):
     e2e = {"value": nq / (e2e_ms * 1e-3), "unit": "claims/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": queries_host.numel() * queries_host.element_size(),
            "d2h_bytes_per_step": out_s.numel() * 4 + out_i.numel() * 8}
+
+    # ---- parity of what the timed steps returned (outside the timed region)
+    parity = parity_check(torch, dist, world, dev, shard, lo, queries, k, last["s"], last["i"], planted_claims, planted_rows)
+    e2e_same = bool(torch.equal(out_i.to(dev), last["i"]))       # the end-to-end path returned the same ids
+    parity["e2e_ids_equal_resident"] = e2e_same
+    parity["ok"] = bool(parity["ok"] and e2e_same)
 
     # ---- BASELINE configs[3]: in-batch InfoNCE, batch 4096 x 768, fused logits + softmax-CE fwd/bwd
     infonce_line = other_configs = None
@@ -451,6 +564,7 @@ def run_b200(args):
                        "l2": "corpus shard (>= 4.8 GB) exceeds the 126 MB L2 every step; no flush needed",
                        "arithmetic": "bf16 operands (tcgen05 kind::f16), fp32 accumulation in TMEM, fp32 scores"},
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clk.summary(), "roofline": roofline,
+            "parity": parity,
         }
         if regimes:
             line["small_batch_regime"] = regimes

@@ -33,7 +33,12 @@ const char* drs_last_error(void);
 
 /* Test / tuning knobs.  "search.cta_group": 0 auto, 1 single CTA (128x256 MMA), 2 CTA pair
  * (256x256 MMA).  "search.num_ctas": 0 auto (all SMs), else the persistent grid size.
- * "search.splits": 0 auto, else the number of corpus splits. */
+ * "search.splits": 0 auto, else the number of corpus splits.
+ * "tune.cooperative" (default 1): the kernels that spin on grid-wide flags (the scan's round barrier, the fused
+ * exchange) are launched cooperatively, so the driver guarantees that the whole grid is resident or refuses; the
+ * scan additionally asks cudaOccupancyMaxActiveClusters and runs WITHOUT the barrier when the grid cannot be
+ * co-resident ("debug.coop_fallbacks" counts those launches).  Calls on one workspace must be issued from one
+ * stream at a time. */
 int drs_set_option(const char* name, int value);
 /* Debug: {flag, tag, block, thread, parity, extra} of the last pipeline wait that timed out (a
  * kernel whose mbarrier wait exceeds a few seconds records this in mapped host memory and traps,
@@ -55,6 +60,9 @@ int drs_debug_max_clusters(int cluster_size, int* out);
  *   corpus   device [nc, dim]   same dtype
  *   out_scores device [nq, k] fp32, descending;  out_ids device [nq, k] int64 = row + id_base
  *   ties are broken by the lower row index; when nc < k the tail is (-inf, -1).
+ * NaN scores (a NaN in a claim or corpus row) are never selected -- they rank below every number, the way numpy's
+ * argpartition / argsort order NaN last in closest_docs (tfidf_doc_ranker.py:70-71); torch.topk would rank them
+ * FIRST.  drs_rerank and drs_search_l2 follow the same rule; a claim whose scores are all NaN returns (-inf, -1).
  * DRS_BF16 / DRS_F16 need dim % 8 == 0 and 16-byte aligned base pointers (TMA); k <= DRS_MAX_K.
  * The running top-k lists hold 16 (or, for 17 <= k on corpora with few splits, 32) entries per (claim, corpus
  * split) in registers.  k beyond the list capacity stays exact: the select emits picks only while no
@@ -114,6 +122,26 @@ int drs_search_sharded_p2p(const void* queries, int64_t nq, const void* corpus, 
                            void* const* peer_ids, void* const* peer_flags, size_t parity_stride_bytes,
                            uint32_t* call_counter, float* out_scores, int64_t* out_ids, void* workspace,
                            size_t workspace_bytes, void* stream);
+
+/*
+ * Query-sliced exchange of per-shard top-k lists for ANY k <= DRS_MAX_K (the fused kernel above serves k <= 16):
+ * rank s owns the claims [s * ceil(nq/world), ...); every rank stores the lists of slice s into rank s's gather
+ * buffer over NVLink peer memory, rank s merges the `world` sorted runs of each of its claims and stores the final
+ * list into every rank's result buffer -- one kernel, three flag-ordered phases, world x fewer bytes and merges per
+ * GPU than gathering every list everywhere (BASELINE configs[4]: 65 536 claims, top-100, 8 GPUs).
+ *   local_scores / local_ids: device [nq, k], this shard's sorted lists with GLOBAL ids (drs_search with id_base;
+ *       (-inf, -1) where the shard has fewer than k rows)
+ *   peer_bases: HOST array of `world` device pointers to each rank's exchange buffer (drs_exchange_sliced_bytes
+ *       bytes, zeroed once, peer-mapped; the same max_nq / max_entries on every rank).  Needs
+ *       ceil(nq/world) * world * k <= max_entries and nq <= max_nq.
+ *   call_counter: device uint32 of this rank, zero at allocation (epochs and buffer parity derive from it).
+ * Collective: every rank makes the same calls.  The result is identical on every rank and equal to the
+ * (score desc, id asc) merge of all shards' lists, i.e. to a single-GPU search of the whole corpus.
+ */
+int drs_exchange_sliced_bytes(int64_t max_nq, int64_t max_entries, int world, size_t* bytes);
+int drs_exchange_sliced(const float* local_scores, const int64_t* local_ids, int64_t nq, int k, int rank, int world,
+                        void* const* peer_bases, int64_t max_nq, int64_t max_entries, uint32_t* call_counter,
+                        float* out_scores, int64_t* out_ids, void* stream);
 
 /*
  * Candidate-restricted re-rank: score each claim against ITS OWN candidate rows only and keep the best k.

@@ -40,6 +40,8 @@ _SIGNATURES = {
     "drs_exchange_flag_bytes": (c_int, [c_i64, c_int, ctypes.POINTER(c_sz)]),
     "drs_search_sharded_p2p": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_vp,
                                        c_sz, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "drs_exchange_sliced_bytes": (c_int, [c_i64, c_i64, c_int, ctypes.POINTER(c_sz)]),
+    "drs_exchange_sliced": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "drs_merge_shards": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp]),
     "drs_infonce_workspace_bytes": (c_int, [c_i64, c_int, c_i64, c_int, ctypes.POINTER(c_sz)]),
     "drs_infonce_forward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_f32, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -60,6 +60,8 @@ struct Options {
   int round_barrier = 1;
   int seed_thresholds = 1;
   int symmetric_grad = 1;
+  int cooperative = 1;     // launch the kernels that spin on grid-wide flags cooperatively (driver-checked co-residency)
+  int coop_fallbacks = 0;  // read-only counter: launches that gave up the round barrier (grid not co-resident)
 } g_opt;
 
 struct DeviceInfo {
@@ -112,11 +114,14 @@ EncodeTiledFn get_encode_fn() {
 // [rows, dim] bf16 row-major; box = 64 (K) x box_rows, 128-byte swizzle, zero fill out of bounds
 inline bool is_16bit(int dtype) { return dtype == DRS_BF16 || dtype == DRS_F16; }
 
-int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int dim, int box_rows, bool f16 = false) {
+// `pitch` = elements from one row to the next (0: dim).  Columns in [dim, pitch) are never read: a box that
+// reaches past `dim` is zero-filled, which is how ragged K extents (prototype counts that are not a multiple
+// of 8) get a 16-byte row pitch without a padded copy.
+int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int dim, int box_rows, bool f16 = false, int64_t pitch = 0) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(DRS_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim) * 2};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(pitch > 0 ? pitch : dim) * 2};
   cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
@@ -268,36 +273,76 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
 }
 
 // ------------------------------------------------------------------ generic GEMM launchers
+// Launch contract for the round barrier (gemm_tc.cuh): the producers spin on a grid-wide counter, which is only safe
+// when every CTA of the grid is resident at the same time.  That is not inferred from "grid <= SM count": the
+// occupancy API is asked how many clusters of this kernel the device holds (it knows about GPC shapes, MIG slices
+// and carve-outs), and the kernel is launched COOPERATIVELY, so the driver either places the whole grid at once --
+// waiting for a kernel on another stream to leave if it must -- or refuses the launch.  If either check fails the
+// scan runs without the barrier (correct, more DRAM traffic) and `debug.coop_fallbacks` counts it.
 template <int CG, class Epi, int BN = 256>
-int launch_gemm_tc(const void* a, const void* b, int kdim, const drs::GemmShape& shp, int grid,
-                   const typename Epi::Params& ep, cudaStream_t st, int64_t a_rows_alloc = 0) {
+int launch_gemm_tc(const void* a, const void* b, int kdim, drs::GemmShape shp, int grid,
+                   const typename Epi::Params& ep, cudaStream_t st, int64_t a_rows_alloc = 0, int64_t pitch_a = 0,
+                   int64_t pitch_b = 0) {
   using Cfg = drs::GemmCfg<CG, BN>;
   CUtensorMap ta, tb;
-  if (int rc = make_tmap_bf16(&ta, a, a_rows_alloc > 0 ? a_rows_alloc : shp.rows_a, kdim, Cfg::BM, shp.f16_operands != 0)) return rc;
-  if (int rc = make_tmap_bf16(&tb, b, shp.rows_b, kdim, Cfg::BN_CTA, shp.f16_operands != 0)) return rc;
+  if (int rc = make_tmap_bf16(&ta, a, a_rows_alloc > 0 ? a_rows_alloc : shp.rows_a, kdim, Cfg::BM, shp.f16_operands != 0, pitch_a)) return rc;
+  if (int rc = make_tmap_bf16(&tb, b, shp.rows_b, kdim, Cfg::BN_CTA, shp.f16_operands != 0, pitch_b)) return rc;
   auto kern = drs::gemm_nt_tc_kernel<CG, Epi, BN>;
-  DRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  static thread_local bool attr_set[64] = {};
+  static thread_local int max_clusters[64] = {};
+  int dev = 0;
+  DRS_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(DRS_ERR_INVALID, "device ordinal %d out of range", dev);
+  if (!attr_set[dev]) {
+    DRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[dev] = true;
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DRS_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, shp, ep));
+  if (shp.round_counter != nullptr) {
+    if (max_clusters[dev] == 0) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { n = -1; (void)cudaGetLastError(); }
+      max_clusters[dev] = n == 0 ? -1 : n;
+    }
+    if (max_clusters[dev] * CG < grid) {   // not all CTAs can be resident at once: no spinning on a grid-wide counter
+      shp.round_counter = nullptr;
+      ++g_opt.coop_fallbacks;
+    } else if (g_opt.cooperative) {
+      attr[1].id = cudaLaunchAttributeCooperative;
+      attr[1].val.cooperative = 1;
+      cfg.numAttrs = 2;
+    }
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, shp, ep);
+  if (e != cudaSuccess && cfg.numAttrs == 2 &&
+      (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported || e == cudaErrorInvalidValue ||
+       e == cudaErrorInvalidConfiguration)) {
+    (void)cudaGetLastError();              // the driver refused to co-schedule the grid: run without the barrier
+    shp.round_counter = nullptr;
+    cfg.numAttrs = 1;
+    ++g_opt.coop_fallbacks;
+    e = cudaLaunchKernelEx(&cfg, kern, ta, tb, shp, ep);
+  }
+  DRS_CUDA(e);
   return DRS_OK;
 }
 template <class Epi>
 int launch_gemm_tc_cg(int cg, const void* a, const void* b, int kdim, const drs::GemmShape& shp, int grid,
-                      const typename Epi::Params& ep, cudaStream_t st) {
-  return cg == 2 ? launch_gemm_tc<2, Epi>(a, b, kdim, shp, grid, ep, st)
-                 : launch_gemm_tc<1, Epi>(a, b, kdim, shp, grid, ep, st);
+                      const typename Epi::Params& ep, cudaStream_t st, int64_t pitch_a = 0, int64_t pitch_b = 0) {
+  return cg == 2 ? launch_gemm_tc<2, Epi>(a, b, kdim, shp, grid, ep, st, 0, pitch_a, pitch_b)
+                 : launch_gemm_tc<1, Epi>(a, b, kdim, shp, grid, ep, st, 0, pitch_a, pitch_b);
 }
 template <class Epi, bool B_KN>
 int launch_gemm_simt(const float* a, long long lda, const float* b, long long ldb, int kdim,
@@ -443,6 +488,8 @@ int drs_set_option(const char* name, int value) {
   else if (!strcmp(name, "tune.round_barrier")) g_opt.round_barrier = value;
   else if (!strcmp(name, "tune.seed_thresholds")) g_opt.seed_thresholds = value;
   else if (!strcmp(name, "tune.symmetric_grad")) g_opt.symmetric_grad = value;
+  else if (!strcmp(name, "tune.cooperative")) g_opt.cooperative = value;
+  else if (!strcmp(name, "debug.coop_fallbacks")) g_opt.coop_fallbacks = value;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;
 }
@@ -458,6 +505,8 @@ int drs_get_option(const char* name, int* value) {
   else if (!strcmp(name, "tune.round_barrier")) *value = g_opt.round_barrier;
   else if (!strcmp(name, "tune.seed_thresholds")) *value = g_opt.seed_thresholds;
   else if (!strcmp(name, "tune.symmetric_grad")) *value = g_opt.symmetric_grad;
+  else if (!strcmp(name, "tune.cooperative")) *value = g_opt.cooperative;
+  else if (!strcmp(name, "debug.coop_fallbacks")) *value = g_opt.coop_fallbacks;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;
 }
@@ -490,7 +539,8 @@ int scan_pass(SearchPlan& p, const void* queries, const void* corpus, int dim, v
   if (is_16bit(p.dtype)) {
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
-    if (g_opt.round_barrier && p.grid <= di.num_sms)   // all CTAs co-resident: the barrier cannot deadlock
+    // requested here, granted by launch_gemm_tc only if the whole grid is co-resident (occupancy query + cooperative launch)
+    if (g_opt.round_barrier && p.grid <= di.num_sms)
       p.shape.round_counter = static_cast<unsigned int*>(workspace);
     if (p.pad_bytes) pad = reinterpret_cast<char*>(ws) + p.cand_bytes;  // zero-padded claims (plan_search explains why)
   }

@@ -59,8 +59,11 @@ struct TopKEpilogue {
         lo = min(lo, min(min(x0, x1), min(x2, x3)));
       }
       for (; j < p.seed_slots; ++j) lo = min(lo, __ldcg(a + j));
-      // strictly below the bound, so that rows TYING it (with a lower index) still enter
-      if (lo != 0u) floor = ordered_to_float(lo - 1u);
+      // strictly below the bound, so that rows TYING it (with a lower index) still enter.  The predecessor of
+      // +0.0 in the ordered domain decodes to -0.0, which `s > thr` cannot tell from +0.0: step once more
+      // (to the largest negative float), or rows scoring exactly 0 -- zero-padded corpus rows, all-zero
+      // claims -- would lose their tie to a later unit.
+      if (lo != 0u) floor = ordered_to_float(lo == 0x80000000u ? lo - 2u : lo - 1u);
     }
     list.reset(floor);
   }

@@ -179,4 +179,170 @@ select_exchange_merge_kernel(const uint64_t* __restrict__ ws, int nq, int nslots
 // One more exchange call is complete on this rank (stream-ordered after select_exchange_merge_kernel).
 __global__ void exchange_done_kernel(uint32_t* calls) { *calls += 1u; }
 
+// =====================================================================================================
+// Query-sliced exchange for any k ("for cfg 5 prefer query-sliced all-to-all + local merge +
+// all-gather of final (Q/g, k)").  With k = 100 and 65 536 claims a rank's lists are 78 MB; gathering every
+// rank's lists everywhere moves world x 78 MB into each GPU and makes every GPU merge all 65 536 claims.  Sliced:
+// rank s owns claims [s * per, (s + 1) * per), per = ceil(nq / world).
+//   phase 1  scatter: each rank stores the lists of slice s straight into rank s's gather buffer (NVLink peer
+//            stores, full lines) and publishes per-(claim block, source) flags on rank s -- no wait anywhere;
+//   phase 2  merge:   rank s waits (per block of its slice) for the flags of all sources, merges the `world` sorted
+//            runs of each claim (k-way merge, one warp per claim, runs staged in shared memory), and stores the
+//            final list into EVERY rank's result buffer, then publishes per-block flags on every rank;
+//   phase 3  collect: each rank waits for the result flags of all blocks of all slices and copies the rows to the
+//            caller's tensors.
+// Bytes over NVLink per rank: (world-1)/world x nq x k x 12 out in phase 1 (8x less than the all-gather at 8
+// ranks) + the final (nq / world) x k x 12 to each peer.  Epochs, parity double-buffering and the call counter
+// work as in the kernel above.  Phase 1 never waits, phase 2 waits only on phase-1 flags and phase 3 only on
+// phase-2 flags, so with all CTAs resident (cooperative launch) the kernel cannot deadlock.
+struct SlicedPeers {
+  char* base[kMaxPeers];   // rank p's symmetric buffer (peer-mapped)
+  size_t flags1_off;       // u32 [blocks per slice][world]   written by sources, read by the slice owner
+  size_t flags2_off;       // u32 [world * blocks per slice]  written by slice owners, read by everyone
+  size_t data_off;         // parity 0 data; parity 1 at + parity_stride
+  size_t parity_stride;
+  size_t gather_i_off;     // within a parity block: gather scores at 0, gather ids here, ...
+  size_t out_s_off;
+  size_t out_i_off;
+  const uint32_t* calls;
+};
+
+constexpr int kSlicedRowsPerBlock = 8;   // claims per block iteration: one per warp
+enum : uint32_t { kTagSlicedWait1 = 7, kTagSlicedWait2 = 8 };
+
+__device__ __forceinline__ void wait_flags_sys(const uint32_t* fl, int count, uint32_t epoch, uint32_t tag, uint32_t extra) {
+  // one warp; lane l < count watches fl[l]
+  const int lane = threadIdx.x & 31;
+  const long long t0 = clock64();
+  for (;;) {
+    bool ok = true;
+    for (int c = lane; c < count; c += 32) ok = ok && static_cast<int32_t>(ld_acquire_sys_u32(fl + c) - epoch) >= 0;
+    if (__all_sync(0xffffffffu, ok)) break;
+    __nanosleep(200);
+    if (clock64() - t0 > kExchangeTimeoutCycles) mbar_hang(tag, epoch, extra);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+exchange_sliced_kernel(const float* __restrict__ local_s, const long long* __restrict__ local_i, int nq, int k,
+                       SlicedPeers peers, int rank, int world, float* __restrict__ out_scores,
+                       long long* __restrict__ out_ids) {
+  extern __shared__ __align__(16) unsigned char xs_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t epoch = *peers.calls + 1u;
+  const size_t par = peers.data_off + ((epoch & 1u) ? peers.parity_stride : 0);
+  const int per = (nq + world - 1) / world;                                   // claims per slice
+  const int bps = (per + kSlicedRowsPerBlock - 1) / kSlicedRowsPerBlock;      // claim blocks per slice
+  const size_t run = static_cast<size_t>(per) * k;                            // one source's lists of one slice
+
+  // ---- phase 1: scatter my lists, slice by slice, into the owners' gather buffers
+  for (int gb = blockIdx.x; gb < world * bps; gb += gridDim.x) {
+    const int dest = gb / bps, b = gb - dest * bps;
+    const int ql = b * kSlicedRowsPerBlock + warp;                            // claim within the slice
+    const int q = dest * per + ql;
+    if (ql < per && q < nq) {
+      float* gs = reinterpret_cast<float*>(peers.base[dest] + par);
+      long long* gi = reinterpret_cast<long long*>(peers.base[dest] + par + peers.gather_i_off);
+      const size_t dst = static_cast<size_t>(rank) * run + static_cast<size_t>(ql) * k;
+      const size_t src = static_cast<size_t>(q) * k;
+      for (int j = lane; j < k; j += 32) {
+        gs[dst + j] = __ldcg(local_s + src + j);
+        gi[dst + j] = __ldcg(local_i + src + j);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys_u32(reinterpret_cast<uint32_t*>(peers.base[dest] + peers.flags1_off) + static_cast<size_t>(b) * world + rank, epoch);
+    }
+  }
+
+  // ---- phase 2: merge the slice I own
+  float* ms = reinterpret_cast<float*>(xs_smem) + static_cast<size_t>(warp) * world * k;                       // [world][k] per warp
+  long long* mi = reinterpret_cast<long long*>(xs_smem + static_cast<size_t>(8) * world * k * sizeof(float)) +
+                  static_cast<size_t>(warp) * world * k;
+  const float* my_gs = reinterpret_cast<const float*>(peers.base[rank] + par);
+  const long long* my_gi = reinterpret_cast<const long long*>(peers.base[rank] + par + peers.gather_i_off);
+  for (int b = blockIdx.x; b < bps; b += gridDim.x) {
+    if (warp == 0)
+      wait_flags_sys(reinterpret_cast<const uint32_t*>(peers.base[rank] + peers.flags1_off) + static_cast<size_t>(b) * world, world,
+                     epoch, kTagSlicedWait1, static_cast<uint32_t>(b));
+    __syncthreads();
+    const int ql = b * kSlicedRowsPerBlock + warp;
+    const int q = rank * per + ql;
+    if (ql < per && q < nq) {
+      for (int c = lane; c < world * k; c += 32) {                      // stage the runs (L2 reads: peers stored them)
+        const int srcr = c / k, j = c - srcr * k;
+        const size_t off = static_cast<size_t>(srcr) * run + static_cast<size_t>(ql) * k + j;
+        ms[c] = __ldcg(my_gs + off);
+        mi[c] = __ldcg(my_gi + off);
+      }
+      __syncwarp();
+      // lane l < world owns run l: head at position pos
+      int pos = 0;
+      float hs = -INFINITY;
+      long long hi = -1;
+      if (lane < world) { hs = ms[lane * k]; hi = mi[lane * k]; }
+      float keep_s = -INFINITY;
+      long long keep_i = -1;
+      for (int r0 = 0; r0 < k; r0 += 32) {
+        const int nr = min(32, k - r0);
+        for (int r = 0; r < nr; ++r) {
+          float bs = hs;
+          long long bi = hi;
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) {                               // runs live in lanes 0..7
+            const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || pair_better(os, oi, bs, bi))) { bs = os; bi = oi; }
+          }
+          bs = __shfl_sync(0xffffffffu, bs, 0);
+          bi = __shfl_sync(0xffffffffu, bi, 0);
+          if (lane == r) { keep_s = bi >= 0 ? bs : -INFINITY; keep_i = bi; }
+          if (bi >= 0 && lane < world && hi == bi && hs == bs) {           // (score, id) pairs are unique: one lane advances
+            ++pos;
+            if (pos < k) { hs = ms[lane * k + pos]; hi = mi[lane * k + pos]; }
+            else { hs = -INFINITY; hi = -1; }
+          }
+        }
+        if (lane < nr) {                                                  // 32 picks: one coalesced store per peer
+          const size_t off = static_cast<size_t>(q) * k + r0 + lane;
+          for (int p = 0; p < world; ++p) {
+            reinterpret_cast<float*>(peers.base[p] + par + peers.out_s_off)[off] = keep_s;
+            reinterpret_cast<long long*>(peers.base[p] + par + peers.out_i_off)[off] = keep_i;
+          }
+        }
+        keep_s = -INFINITY;
+        keep_i = -1;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < world) {
+      __threadfence_system();
+      st_release_sys_u32(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x] + peers.flags2_off) + static_cast<size_t>(rank) * bps + b, epoch);
+    }
+  }
+
+  // ---- phase 3: collect every slice's results from my result buffer into the caller's tensors
+  const float* rs = reinterpret_cast<const float*>(peers.base[rank] + par + peers.out_s_off);
+  const long long* ri = reinterpret_cast<const long long*>(peers.base[rank] + par + peers.out_i_off);
+  for (int gb = blockIdx.x; gb < world * bps; gb += gridDim.x) {
+    if (warp == 0)
+      wait_flags_sys(reinterpret_cast<const uint32_t*>(peers.base[rank] + peers.flags2_off) + gb, 1, epoch, kTagSlicedWait2,
+                     static_cast<uint32_t>(gb));
+    __syncthreads();
+    const int s = gb / bps, b = gb - s * bps;
+    const int q0 = s * per + b * kSlicedRowsPerBlock;
+    const int q1 = min(min(q0 + kSlicedRowsPerBlock, (s + 1) * per), nq);
+    if (q1 > q0) {
+      const size_t lo = static_cast<size_t>(q0) * k, n = static_cast<size_t>(q1 - q0) * k;
+      for (size_t e = threadIdx.x; e < n; e += blockDim.x) {
+        out_scores[lo + e] = __ldcg(rs + lo + e);
+        out_ids[lo + e] = __ldcg(ri + lo + e);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace drs

@@ -396,11 +396,13 @@ struct StoreEpilogue {
 // copy are both written with full 128-byte lines (a plain "one thread per element" transpose writes
 // 2-byte elements 16 KB apart and took 60 us for the 8192 x 768 operand; this takes ~10).
 //   src: [R][C] fp32 row-major; rows [0, split) come from s0, rows [split, R) from s1 (cat(q, k), :61)
-//   any of: o32 [R][C] fp32, obf [R][C] bf16, o32_t [C][R] fp32, obf_t [C][R] bf16
+//   any of: o32 [R][ld_o] fp32, obf [R][ld_o] bf16, o32_t [C][ld_t] fp32, obf_t [C][ld_t] bf16
+//   (ld_o >= C, ld_t >= R: row pitches in elements; the pad columns are never written nor read -- the tensor maps
+//    that read these buffers stop at the true extent and zero-fill beyond it)
 __global__ void __launch_bounds__(256)
 pack_transpose_kernel(const float* __restrict__ s0, const float* __restrict__ s1, long long split, long long R, long long C,
                       float* __restrict__ o32, __nv_bfloat16* __restrict__ obf, float* __restrict__ o32_t,
-                      __nv_bfloat16* __restrict__ obf_t) {
+                      __nv_bfloat16* __restrict__ obf_t, long long ld_o, long long ld_t) {
   __shared__ float tile[32][33];
   const long long tiles_c = (C + 31) / 32, tiles_r = (R + 31) / 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -412,8 +414,8 @@ pack_transpose_kernel(const float* __restrict__ s0, const float* __restrict__ s1
       float x = 0.f;
       if (r < R && c < C) {
         x = r < split ? s0[r * C + c] : s1[(r - split) * C + c];
-        if (o32) o32[r * C + c] = x;
-        if (obf) obf[r * C + c] = __float2bfloat16_rn(x);
+        if (o32) o32[r * ld_o + c] = x;
+        if (obf) obf[r * ld_o + c] = __float2bfloat16_rn(x);
       }
       tile[ty + 8 * i][tx] = x;
     }
@@ -424,8 +426,8 @@ pack_transpose_kernel(const float* __restrict__ s0, const float* __restrict__ s1
         const long long c = c0 + ty + 8 * i, r = r0 + tx;  // consecutive threads -> consecutive r
         if (r < R && c < C) {
           const float x = tile[tx][ty + 8 * i];
-          if (o32_t) o32_t[c * R + r] = x;
-          if (obf_t) obf_t[c * R + r] = __float2bfloat16_rn(x);
+          if (o32_t) o32_t[c * ld_t + r] = x;
+          if (obf_t) obf_t[c * ld_t + r] = __float2bfloat16_rn(x);
         }
       }
     }

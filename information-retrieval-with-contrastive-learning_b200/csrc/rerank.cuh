@@ -91,7 +91,9 @@ rerank_kernel(const T* __restrict__ queries, const T* __restrict__ corpus, const
     uint64_t key = 0ull;
     if (id >= 0 && id < nc) {
       const float s = warp_row_dot<T, VEC>(corpus + static_cast<size_t>(id) * dim, qs, dim, lane);
-      key = make_key(s, static_cast<uint32_t>(id));
+      // a NaN score is never a candidate, exactly as in the search epilogue (`s > thr` is false for NaN) and as
+      // numpy's argpartition / argsort order NaN last in closest_docs (tfidf_doc_ranker.py:70-71)
+      if (s == s) key = make_key(s, static_cast<uint32_t>(id));
     }
     if (lane == 0) keys[c] = key;
   }

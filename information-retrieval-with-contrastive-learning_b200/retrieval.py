@@ -320,12 +320,16 @@ class DenseIndex:
         if doc_ids is not None:
             self.doc_dict = ({d: i for i, d in enumerate(doc_ids)}, list(doc_ids))
 
-    # -- tfidf_doc_ranker.py:52-58
+    # -- tfidf_doc_ranker.py:52-58.  Rows are GLOBAL on both sides (a shard's first row is `id_base`), so
+    #    get_doc_index(get_doc_id(r)) == r for every id `search` returns, sharded or not.
     def get_doc_index(self, doc_id):
-        return self.doc_dict[0][doc_id] if self.doc_dict else int(doc_id)
+        return (self.doc_dict[0][doc_id] + self.id_base) if self.doc_dict else int(doc_id)
 
     def get_doc_id(self, doc_index):
-        return self.doc_dict[1][doc_index] if self.doc_dict else int(doc_index)
+        local = int(doc_index) - self.id_base
+        if not 0 <= local < self.num_docs:
+            raise IndexError(f"row {doc_index} is not in this shard [{self.id_base}, {self.id_base + self.num_docs})")
+        return self.doc_dict[1][local] if self.doc_dict else int(doc_index)
 
     def search(self, queries: torch.Tensor, k: int = 1, profile: Optional[list] = None):
         """queries [nq, D] on any device (host tensors are copied in) -> device (scores, ids)."""
@@ -368,7 +372,7 @@ class DenseIndex:
         out = []
         for s_row, i_row in zip(scores, ids):
             keep = i_row >= 0
-            out.append(([self.get_doc_id(int(i) - self.id_base) for i in i_row[keep]], s_row[keep]))
+            out.append(([self.get_doc_id(int(i)) for i in i_row[keep]], s_row[keep]))
         return out
 
 
@@ -379,9 +383,10 @@ class DenseDocRanker(DenseIndex):
     (src/contrastor/contrastive_module.py:96-100), the call the commented block at
     src/evaluation.py:110-111 makes.  Tensors are accepted too (then no encoder is needed)."""
 
-    def __init__(self, index_path: str, encoder=None, *, device=None, rank: int = 0, world_size: int = 1, strict: bool = True):
+    def __init__(self, index_path: str, encoder=None, *, device=None, rank: int = 0, world_size: int = 1, strict: bool = True,
+                 verify: bool = False):
         from .store import load_dense_index
-        index, meta = load_dense_index(index_path, device=device, rank=rank, world_size=world_size)
+        index, meta = load_dense_index(index_path, device=device, rank=rank, world_size=world_size, verify=verify)
         self.__dict__.update(index.__dict__)
         self.metadata = meta
         self.encoder = encoder
@@ -438,6 +443,30 @@ class _PeerExchange:
         self.flag_ptrs = arr(*self.ptrs)
 
 
+class _SlicedExchange:
+    """Symmetric buffer for the query-sliced exchange (csrc/exchange.cuh::exchange_sliced_kernel): per rank
+
+        [ flags1 | flags2 | parity 0: gather scores, gather ids, result scores, result ids | parity 1: ... ]
+
+    laid out by the library (drs_exchange_sliced_bytes) from (max_nq, max_entries, world)."""
+
+    MAX_NQ = 1 << 18
+
+    def __init__(self, group, device, world, rank, max_entries):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank, self.max_entries = world, rank, int(max_entries)
+        need = ctypes.c_size_t(0)
+        _lib.check(_lib.load().drs_exchange_sliced_bytes(self.MAX_NQ, self.max_entries, world, ctypes.byref(need)))
+        self.buf = symm.empty(need.value, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.handle.barrier()                         # every rank's flags are zero before anyone publishes
+        self.bases = (ctypes.c_void_p * world)(*[int(p) for p in self.handle.buffer_ptrs])
+        self.calls = torch.zeros(1, dtype=torch.int32, device=device)
+
+
 class ShardedDenseIndex:
     """Row-sharded corpus over the ranks of a torch.distributed group (one process per GPU).
 
@@ -445,9 +474,11 @@ class ShardedDenseIndex:
     The per-rank (score, global id) lists are then exchanged and merged by (score desc, id asc), which
     makes the result identical to a single-GPU search of the whole corpus.  Two exchanges:
 
-    * ``exchange='p2p'``: ONE kernel per search selects the shard's top-k, stores it into every peer's
-      buffer over NVLink peer memory, waits on per-claim-block flags and merges (csrc/exchange.cuh);
-      needs the NCCL backend's symmetric memory, k <= 16, <= 8 ranks, no empty shard;
+    * ``exchange='p2p'`` (NVLink peer memory, csrc/exchange.cuh; needs the NCCL backend's symmetric memory, <= 8
+      ranks, no empty shard).  k <= 16: ONE kernel per search selects the shard's top-k, stores it into every peer's
+      buffer, waits on per-claim-block flags and merges.  Larger k (BASELINE configs[4]: top-100): the QUERY-SLICED
+      kernel -- rank s receives only the lists of its slice of the claims, merges them and stores the final lists
+      into every rank's result buffer (world x fewer bytes and merges per GPU than gathering everything everywhere);
     * ``exchange='nccl'``: select, ``all_gather_into_tensor`` of scores and ids, merge kernel (any backend).
 
     ``exchange='auto'`` (default) takes 'p2p' when its conditions hold, else 'nccl'.
@@ -476,6 +507,7 @@ class ShardedDenseIndex:
         self.exchange = "p2p" if (p2p_ok and exchange != "nccl") else "nccl"
         self._exchange_requested = exchange
         self._peer = None
+        self._sliced = None
 
     def _peer_exchange(self, entries: int):
         """The symmetric buffers, (re)allocated collectively -- every rank sees the same `entries`.  Returns
@@ -497,25 +529,78 @@ class ShardedDenseIndex:
             self._peer = peer
         return self._peer
 
-    def search(self, queries: torch.Tensor, k: int = 1, profile: Optional[list] = None):
+    def _sliced_exchange(self, entries: int):
+        """The query-sliced exchange buffers, (re)allocated collectively like `_peer_exchange`."""
+        if self._sliced is None or self._sliced.max_entries < entries:
+            cap = max(entries, 1 << 20) if self._sliced is None else max(entries, 2 * self._sliced.max_entries)
+            ok, err = 1, None
+            try:
+                sl = _SlicedExchange(self.group, self.local.device, self.world, self.rank, cap)
+            except Exception as e:  # noqa: BLE001
+                ok, err, sl = 0, e, None
+            flag = torch.tensor([ok], device=self.local.device)
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
+            if not int(flag.item()):
+                if self._exchange_requested == "p2p":
+                    raise RuntimeError(f"exchange='p2p': peer memory could not be mapped on every rank ({err})")
+                self.exchange, self._sliced = "nccl", None
+                return None
+            self._sliced = sl
+        return self._sliced
+
+    def search(self, queries: torch.Tensor, k: int = 1, profile: Optional[list] = None, timing: Optional[dict] = None):
+        """``timing``: optional dict; CUDA event pairs are stored under 'local' (scan + select of this shard) and
+        'exchange' (the exchange + merge) for the paths that run them as separate launches (k > 16, NCCL)."""
         kk = min(int(k), self.total_rows)
         nq = queries.shape[0]
         if self.exchange == "p2p" and 0 < kk <= 16 and 0 < nq <= _PeerExchange.MAX_NQ:
             if self._peer_exchange(nq * kk) is not None:
                 return self._search_p2p(queries, kk, profile)
+        dev = self.local.device
+
+        def mark():
+            if timing is None:
+                return None
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(dev))
+            return ev
+
+        t0 = mark()
         s, i = (self.local.search(queries, min(kk, max(self.local.num_docs, 1)), profile=profile)
                 if self.local.num_docs else (None, None))
-        dev = self.local.device
         # fixed-size slots so every rank contributes the same number of bytes
-        slot_s = torch.full((nq, kk), float("-inf"), dtype=torch.float32, device=dev)
-        slot_i = torch.full((nq, kk), -1, dtype=torch.int64, device=dev)
-        if s is not None:
-            slot_s[:, : s.shape[1]] = s
-            slot_i[:, : i.shape[1]] = i
+        if s is not None and s.shape[1] == kk:
+            slot_s, slot_i = s, i
+        else:
+            slot_s = torch.full((nq, kk), float("-inf"), dtype=torch.float32, device=dev)
+            slot_i = torch.full((nq, kk), -1, dtype=torch.int64, device=dev)
+            if s is not None:
+                slot_s[:, : s.shape[1]] = s
+                slot_i[:, : i.shape[1]] = i
+        t1 = mark()
         if self.world == 1:
             return slot_s, slot_i
-        all_s, all_i = all_gather_topk(slot_s, slot_i, self.group)
-        return merge_shards(all_s, all_i)
+        out = None
+        per = -(-nq // self.world)
+        if self.exchange == "p2p" and 0 < nq <= _SlicedExchange.MAX_NQ and kk <= _lib.DRS_MAX_K:
+            sl = self._sliced_exchange(per * self.world * kk)
+            if sl is not None:
+                out_s = torch.empty(nq, kk, dtype=torch.float32, device=dev)
+                out_i = torch.empty(nq, kk, dtype=torch.int64, device=dev)
+                with torch.cuda.device(dev):
+                    _lib.check(_lib.load().drs_exchange_sliced(slot_s.data_ptr(), slot_i.data_ptr(), nq, kk, self.rank, self.world,
+                                                               sl.bases, sl.MAX_NQ, sl.max_entries, sl.calls.data_ptr(),
+                                                               out_s.data_ptr(), out_i.data_ptr(),
+                                                               torch.cuda.current_stream(dev).cuda_stream))
+                out = (out_s, out_i)
+        if out is None:
+            all_s, all_i = all_gather_topk(slot_s, slot_i, self.group)
+            out = merge_shards(all_s, all_i)
+        t2 = mark()
+        if timing is not None:
+            timing.setdefault("local", []).append((t0, t1))
+            timing.setdefault("exchange", []).append((t1, t2))
+        return out
 
     def _search_p2p(self, queries: torch.Tensor, kk: int, profile: Optional[list]):
         loc = self.local

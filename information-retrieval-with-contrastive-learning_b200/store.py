@@ -13,7 +13,13 @@ two calls here, with a layout made for the GPU:
   a shard is ``np.memmap``-ed and streamed to HBM through a pinned staging buffer, no parsing;
 * any contiguous row range can be loaded on its own, so rank r of g reads only ``shard_bounds(N, r, g)``
   (SURVEY.md 8e) -- a 25M x 768 bf16 corpus (38.4 GB) never has to fit in host memory;
-* a CRC32 of the payload guards against truncated copies.
+* the header carries a CRC32 of the payload; ``load_dense_index(..., verify=True)`` / ``verify(filename)``
+  recompute it (a full read of the file, so it is opt-in: a rank that loads one shard of a 38 GB corpus
+  should not have to read the other seven).  Truncation is always detected (sizes are checked on load).
+
+TRUST: the metadata block is a pickle, like the reference's ``np.load(..., allow_pickle=True)``
+(retriever/utils.py:33).  Unpickling runs code chosen by whoever wrote the file -- load index files only
+from sources you would run code from.
 """
 from __future__ import annotations
 
@@ -100,6 +106,9 @@ def verify(filename: str, chunk_bytes: int = 1 << 26) -> bool:
     return (crc & 0xFFFFFFFF) == h["crc32"]
 
 
+_verify_file = verify      # load_dense_index has a keyword of the same name
+
+
 def load_rows(filename: str, lo: int = 0, hi: Optional[int] = None, device=None, chunk_rows: int = 1 << 18) -> torch.Tensor:
     """Rows [lo, hi) of the stored matrix as a tensor of the stored dtype.  ``device=None`` -> host tensor
     (I/O only; the engine itself has no CPU path); a CUDA device -> memory-mapped read streamed through a
@@ -138,11 +147,18 @@ def load_rows(filename: str, lo: int = 0, hi: Optional[int] = None, device=None,
     return out
 
 
-def load_dense_index(filename: str, device=None, rank: int = 0, world_size: int = 1):
+def load_dense_index(filename: str, device=None, rank: int = 0, world_size: int = 1, verify: bool = False):
     """utils.py:32-36 for a dense corpus: ``(DenseIndex, metadata)``.  With ``world_size > 1`` the index
-    holds only this rank's row shard (``shard_bounds``) with its global ``id_base``."""
+    holds only this rank's row shard (``shard_bounds``) with its global ``id_base``.  ``verify=True`` recomputes
+    the payload CRC32 first (reads the whole file) and raises on a mismatch; the file size is always checked."""
+    import os
     from .retrieval import DenseIndex, shard_bounds
     h = read_header(filename)
+    expect = h["payload_offset"] + h["payload_bytes"] + h["metadata_bytes"]
+    if os.path.getsize(filename) < expect:
+        raise RuntimeError(f"{filename}: truncated ({os.path.getsize(filename)} bytes, header promises {expect})")
+    if verify and not _verify_file(filename):
+        raise RuntimeError(f"{filename}: payload CRC32 mismatch (corrupted index file)")
     lo, hi = shard_bounds(h["rows"], rank, world_size)
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())

@@ -32,6 +32,7 @@ import torch
 
 REF = os.environ.get("DRS_REFERENCE_ROOT", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
 
 
 def _unit(x, dim=1):
@@ -82,17 +83,16 @@ def gen_infonce():
         def __call__(self, population, r):
             return sorted(population)[:r]
 
-    for name, n, d, ncl, r in [("n16_d32", 16, 32, [24, 40], 6), ("n64_d128", 64, 128, [96], 20)]:
-        g = torch.Generator().manual_seed(1337)
-        q = _unit(torch.randn(n, d, generator=g)).requires_grad_(True)
-        index = torch.randperm(4 * n, generator=g)[:n]
-        cluster_result = {"emb2cluster": [], "centroids": [], "density": []}
-        for c in ncl:
-            e2c = torch.randint(0, c, (4 * n,), generator=g)
-            e2c[0] = c - 1                      # make emb2cluster.max() == c-1 as in a real run
-            cluster_result["emb2cluster"].append(e2c)
-            cluster_result["centroids"].append(_unit(torch.randn(c, d, generator=g)))
-            cluster_result["density"].append(torch.rand(c, generator=g) * 0.1 + 0.02)
+    from proto_inputs import make_inputs, checksum
+
+    # (name, N, D, clusters per set, r, compact): N + r = 22 / 84 (ragged: not a multiple of 8), 88 (aligned), and the
+    # reference's own shapes -- batch 128, 128-d, 3072 negatives (config.yaml:7,29-30,87) -> 3200 columns.  `compact`
+    # fixtures store q, index and the outputs only; the test regenerates the cluster sets from the seed.
+    for name, n, d, ncl, r, compact in [("n16_d32", 16, 32, [24, 40], 6, False), ("n64_d128", 64, 128, [96], 20, False),
+                                        ("n64_d128_r24", 64, 128, [96, 160], 24, False),
+                                        ("n128_d128_r3072", 128, 128, [4096, 6144], 3072, True)]:
+        q, index, cluster_result = make_inputs(n, d, ncl, seed=1337)
+        q.requires_grad_(True)
         crit = ref_loss.NCELoss({"temperature": 0.05, "cluster": {"num_cluster": ncl, "num_neg_proto": r}})
         saved = ref_loss.sample
         ref_loss.sample = _FixedSample()
@@ -103,10 +103,13 @@ def gen_infonce():
         loss.backward()
         out = dict(q=q.detach().numpy(), index=index.numpy(), loss=loss.detach().numpy(), dq=q.grad.numpy(),
                    num_sets=np.int64(len(ncl)), num_neg_proto=np.int64(r))
-        for s, c in enumerate(ncl):
-            out[f"emb2cluster{s}"] = cluster_result["emb2cluster"][s].numpy()
-            out[f"centroids{s}"] = cluster_result["centroids"][s].numpy()
-            out[f"density{s}"] = cluster_result["density"][s].numpy()
+        if compact:
+            out.update(seed=np.int64(1337), num_cluster=np.array(ncl, dtype=np.int64), checksum=checksum(cluster_result))
+        else:
+            for s, c in enumerate(ncl):
+                out[f"emb2cluster{s}"] = cluster_result["emb2cluster"][s].numpy()
+                out[f"centroids{s}"] = cluster_result["centroids"][s].numpy()
+                out[f"density{s}"] = cluster_result["density"][s].numpy()
         np.savez_compressed(os.path.join(HERE, f"proto_{name}.npz"), **out)
 
 

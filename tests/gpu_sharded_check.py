@@ -1,8 +1,11 @@
 #!/usr/bin/env python
-"""Multi-GPU check (run under torchrun, one rank per GPU, NCCL): the sharded search
-(per-rank fused kernel -> all-gather over NVLink -> on-GPU merge) must equal the single-GPU
-search of the whole corpus bit for bit, and the CPU oracle on a claim sample.
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/gpu_sharded_check.py"""
+"""Multi-GPU check (run under torchrun, one rank per GPU, NCCL backend for the rendezvous): the sharded search --
+per-rank scan, then ONE exchange step: the fused select + NVLink peer-memory exchange + merge kernel (k <= 16), the
+query-sliced peer-memory exchange (k > 16), or NCCL all-gather + merge -- must equal the single-GPU search of the
+whole corpus bit for bit, and the CPU oracle on a claim sample.  `--quick` skips the latency section.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/gpu_sharded_check.py
+Launched by tests/test_robustness_gpu.py::test_sharded_search_under_torchrun_equals_single_gpu when the box has
+>= 2 GPUs; a log of an 8-GPU run is kept under profiles/."""
 import os
 import sys
 
@@ -17,8 +20,11 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
+QUICK = "--quick" in sys.argv
 ok = True
-for nq, nc, dim, k in [(300, 100003, 128, 10), (1000, 1000000, 768, 10), (64, 7, 64, 5)]:
+# (the k = 100 and k = 33 cases take the query-sliced exchange; 9 claims over 8 ranks leaves ragged / empty slices)
+for nq, nc, dim, k in [(300, 100003, 128, 10), (1000, 1000000, 768, 10), (64, 7, 64, 5), (1000, 300000, 128, 100),
+                       (9, 50000, 64, 33), (5000, 200000, 64, 256)]:
     g = torch.Generator(device=dev).manual_seed(1337)            # same data on every rank
     corpus = torch.nn.functional.normalize(torch.randn(nc, dim, generator=g, device=dev), dim=1).bfloat16()
     if nc > 100:
@@ -38,6 +44,12 @@ for nq, nc, dim, k in [(300, 100003, 128, 10), (1000, 1000000, 768, 10), (64, 7,
     if nq > 64:                                                                                     # a smaller batch on the same buffers
         s3, i3 = index.search(queries[:17], k)
         same = same and torch.equal(i3, fi[:17]) and torch.equal(s3, fs[:17])
+    if nq == 1000 and k == 100:                                                                     # buffer regrowth between calls
+        big = torch.cat([queries] * 12)
+        s4, i4 = index.search(big, k)
+        same = same and torch.equal(i4[-nq:], fi) and torch.equal(s4[:nq], fs)
+        s5, i5 = index.search(queries, k)
+        same = same and torch.equal(i5, fi) and torch.equal(s5, fs)
     rv, ri = dense_topk.search(queries[:32].cpu(), corpus.cpu(), k)
     oracle_ok = torch.equal(i[:32].cpu()[:, 0], ri[:, 0]) and torch.allclose(s[:32].cpu(), rv, rtol=2e-2, atol=1e-4)
     tie_ok = nc <= 100 or i[0, :2].tolist() == [3, nc - 1]
@@ -75,6 +87,39 @@ dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(f"sharded x{world} [{idx.exchange}] CUDA graph replay of the fused exchange: {bool(flag.item())}", flush=True)
 ok = ok and bool(flag.item())
+
+if QUICK:
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+# top-100 exchange at a BASELINE configs[4]-like shape: 65 536 claims, sliced peer-memory kernel vs NCCL all-gather + merge
+nc, dim, k = 100_000 * world, 128, 100
+g = torch.Generator(device=dev).manual_seed(1337 + rank)
+lo, hi = drs_b200.shard_bounds(nc, rank, world)
+shard = torch.nn.functional.normalize(torch.randn(hi - lo, dim, generator=g, device=dev), dim=1).bfloat16()
+q = torch.nn.functional.normalize(torch.randn(65536, dim, generator=torch.Generator(device=dev).manual_seed(5), device=dev), dim=1).bfloat16()
+res = {}
+for mode in ("p2p", "nccl"):
+    idx = drs_b200.ShardedDenseIndex(shard, nc, device=dev, exchange=mode)
+    for _ in range(2):
+        out = idx.search(q, k)
+    timing = {}
+    dist.barrier()
+    torch.cuda.synchronize()
+    for _ in range(5):
+        out = idx.search(q, k, timing=timing)
+    torch.cuda.synchronize()
+    loc = sum(a.elapsed_time(b) for a, b in timing["local"]) / 5
+    ex = sum(a.elapsed_time(b) for a, b in timing["exchange"]) / 5
+    t = torch.tensor([loc, ex], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res[mode] = (t.tolist(), out)
+eq = torch.equal(res["p2p"][1][0], res["nccl"][1][0]) and torch.equal(res["p2p"][1][1], res["nccl"][1][1])
+ok = ok and eq
+if rank == 0:
+    print(f"top-100 exchange x{world}, 65536 claims: sliced p2p {res['p2p'][0][1]:.3f} ms vs nccl all-gather + merge {res['nccl'][0][1]:.3f} ms "
+          f"(local scan + select {res['p2p'][0][0]:.3f} ms), same={eq}", flush=True)
 
 # latency of the exchange in the small-batch regime: fused p2p kernel vs select + 2 all-gathers + merge
 nc, dim, k = 4_000_000, 768, 10

@@ -15,6 +15,22 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 DEV = "cuda:0"
 
 
+def _assert_rows_close(got, ref, precision):
+    """Every gradient ROW on its own scale (a max-abs bar over the matrix would let small rows be arbitrarily wrong):
+    relative L2 error <= 3e-2 and cosine >= 0.9995 on the bf16 path (a CPU emulation of the bf16 roundings gives
+    <= 1.8e-2 / >= 0.99995 on these fixtures), 2e-4 / 0.999999 on the fp32 path.  Rows whose reference norm is below
+    1e-6 of the largest row are compared on that floor."""
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    rn = np.linalg.norm(ref, axis=1)
+    floor = max(rn.max(), 1e-30) * 1e-6
+    rel = np.linalg.norm(got - ref, axis=1) / np.maximum(rn, floor)
+    cos = (got * ref).sum(1) / np.maximum(np.linalg.norm(got, axis=1) * rn, 1e-300)
+    rtol, ctol = (3e-2, 0.9995) if precision == "bf16" else (2e-4, 0.999999)
+    assert rel.max() <= rtol, f"worst row: relative L2 error {rel.max():.3e} at row {rel.argmax()}"
+    live = rn > floor
+    assert cos[live].min() >= ctol, f"worst row: cosine {cos[live].min():.6f} at row {np.flatnonzero(live)[cos[live].argmin()]}"
+
+
 def _run(q, k, queue, temp, precision, cg=0, upstream=1.0):
     q = torch.as_tensor(q).to(DEV).requires_grad_(True)
     k = torch.as_tensor(k).to(DEV).requires_grad_(True)
@@ -40,6 +56,8 @@ def test_fp32_path_matches_reference_golden(path):
     scale = max(np.abs(z["dq"]).max(), np.abs(z["dk"]).max())
     np.testing.assert_allclose(dq.numpy(), z["dq"], rtol=0, atol=1e-4 * scale)
     np.testing.assert_allclose(dk.numpy(), z["dk"], rtol=0, atol=1e-4 * scale)
+    _assert_rows_close(dq.numpy(), z["dq"], "fp32")
+    _assert_rows_close(dk.numpy(), z["dk"], "fp32")
 
 
 @pytest.mark.parametrize("cg", [1, 2])
@@ -53,6 +71,8 @@ def test_bf16_tcgen05_path_matches_reference_golden(name, cg):
     scale = max(np.abs(z["dq"]).max(), np.abs(z["dk"]).max())
     np.testing.assert_allclose(dq.numpy(), z["dq"], rtol=0, atol=3e-2 * scale)
     np.testing.assert_allclose(dk.numpy(), z["dk"], rtol=0, atol=3e-2 * scale)
+    _assert_rows_close(dq.numpy(), z["dq"], "bf16")
+    _assert_rows_close(dk.numpy(), z["dk"], "bf16")
 
 
 @pytest.mark.parametrize("precision,n,dim,klen", [("fp32", 50, 100, 37), ("fp32", 300, 128, 0), ("bf16", 512, 768, 0),
@@ -87,6 +107,8 @@ def test_config4_full_size_forward_backward():
     scale = rdq.abs().max().item()
     assert (dq - rdq).abs().max().item() <= 3e-2 * scale
     assert (dk - rdk).abs().max().item() <= 3e-2 * scale
+    _assert_rows_close(dq.numpy(), rdq.numpy(), "bf16")
+    _assert_rows_close(dk.numpy(), rdk.numpy(), "bf16")
 
 
 def test_module_is_stateless_and_k_no_grad_ok():
@@ -115,30 +137,27 @@ def test_moco_infonce_matches_reference_golden(path, precision):
     scale = max(np.abs(z["dq"]).max(), np.abs(z["dk"]).max())
     np.testing.assert_allclose(q.grad.cpu().numpy(), z["dq"], rtol=0, atol=gtol * scale)
     np.testing.assert_allclose(k.grad.cpu().numpy(), z["dk"], rtol=0, atol=gtol * scale)
+    _assert_rows_close(q.grad.cpu().numpy(), z["dq"], precision)
+    _assert_rows_close(k.grad.cpu().numpy(), z["dk"], precision)
 
 
 def _proto_inputs(z):
     """the selection of contrastive_loss.py:101-112,122-123 with make_golden.py's fixed sampler"""
-    index, r = z["index"], int(z["num_neg_proto"])
-    protos, temps = [], []
-    for s in range(int(z["num_sets"])):
-        e2c, cen, den = z[f"emb2cluster{s}"], z[f"centroids{s}"], z[f"density{s}"]
-        pos_id = e2c[index]
-        neg = sorted(set(range(int(e2c.max()))) - set(pos_id.tolist()))[:r]
-        ids = np.concatenate([pos_id, np.array(neg, dtype=np.int64)])
-        protos.append(torch.from_numpy(cen[ids]).to(DEV))
-        temps.append(torch.from_numpy(den[ids]).to(DEV))
-    return protos, temps
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from proto_inputs import selected_from_fixture
+    protos, temps = selected_from_fixture(z)
+    return [torch.from_numpy(p).to(DEV) for p in protos], [torch.from_numpy(t).to(DEV) for t in temps]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "proto_*.npz"))))
 def test_proto_nce_matches_reference_golden(path, precision):
-    """NCELoss._compute_proto_loss (contrastive_loss.py:112-134) vs the reference's own outputs."""
+    """NCELoss._compute_proto_loss (contrastive_loss.py:112-134) vs the reference's own outputs.  Prototype counts
+    22 and 84 (ragged), 88, and the reference's own 128 + 3072 = 3200 (config.yaml:29-30,87), all on both paths:
+    the tcgen05 path takes any count (padded pitch + tensor maps that stop at the true extent)."""
     z = np.load(path)
     protos, temps = _proto_inputs(z)
-    if precision == "bf16" and any(p.shape[0] % 8 for p in protos):
-        pytest.skip("bf16 path needs a prototype count that is a multiple of 8")
     q = torch.from_numpy(z["q"]).to(DEV).requires_grad_(True)
     loss = drs_b200.proto_nce_loss(q, protos, temps, precision)
     (loss * 2.0).backward()
@@ -146,6 +165,7 @@ def test_proto_nce_matches_reference_golden(path, precision):
     assert abs(loss.item() - float(z["loss"])) <= tol * abs(float(z["loss"])) + 1e-5
     scale = np.abs(z["dq"]).max() * 2.0
     np.testing.assert_allclose(q.grad.cpu().numpy(), 2.0 * z["dq"], rtol=0, atol=gtol * scale)
+    _assert_rows_close(q.grad.cpu().numpy(), 2.0 * z["dq"], precision)
 
 
 def test_nceloss_with_cluster_result_adds_proto_loss():

@@ -43,18 +43,12 @@ def test_moco_infonce_matches_reference(path):
 
 def _proto_inputs(z):
     """the selection contrastive_loss.py:101-112,122-123 makes, with the fixed sampler of
-    make_golden.py (sorted(set)[:r])"""
-    index = z["index"]
-    r = int(z["num_neg_proto"])
-    protos, temps = [], []
-    for s in range(int(z["num_sets"])):
-        e2c, cen, den = z[f"emb2cluster{s}"], z[f"centroids{s}"], z[f"density{s}"]
-        pos_id = e2c[index]
-        neg = sorted(set(range(int(e2c.max()))) - set(pos_id.tolist()))[:r]
-        ids = np.concatenate([pos_id, np.array(neg, dtype=np.int64)])
-        protos.append(_t(cen[ids]))
-        temps.append(_t(den[ids]))
-    return protos, temps
+    make_golden.py (sorted(set)[:r]); tests/golden/proto_inputs.py"""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from proto_inputs import selected_from_fixture
+    protos, temps = selected_from_fixture(z)
+    return [_t(p) for p in protos], [_t(t) for t in temps]
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "proto_*.npz"))))
