@@ -483,18 +483,38 @@ def run_b200(args):
     prof = []
 
     last = {}
+    # k > 16 on several GPUs: local scan + select passes, then the exchange as its own launch -- time both parts
+    timing = {} if (world > 1 and k > 16) else None
 
     def step_resident():
-        last["s"], last["i"] = index.search(queries, k, profile=prof)
+        if timing is not None:
+            last["s"], last["i"] = index.search(queries, k, profile=prof, timing=timing)
+        else:
+            last["s"], last["i"] = index.search(queries, k, profile=prof)
 
     for _ in range(args.warmup):
         step_resident()
     prof.clear()
+    if timing is not None:
+        timing.clear()
     with ClockSampler(local_rank) as clk:
         total_ms = timed_loop(step_resident, args.steps)
     ms_per_step = total_ms / args.steps
     # k > 16 runs adaptive passes (scan + select pairs): no single scan launch to bracket, use the whole step
     kern_ms = sum(a.elapsed_time(b) for a, b in prof) / len(prof) if prof else ms_per_step
+    exchange_rec = None
+    if timing:
+        loc = sum(a.elapsed_time(b) for a, b in timing["local"]) / len(timing["local"])
+        exc = sum(a.elapsed_time(b) for a, b in timing["exchange"]) / len(timing["exchange"])
+        t = torch.tensor([loc, exc], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        loc, exc = t.tolist()
+        kern_ms = loc
+        per = -(-nq // world)
+        exchange_rec = {"kind": ("query-sliced NVLink peer-memory exchange + merge (exchange_sliced_kernel)" if index.exchange == "p2p"
+                                 else "NCCL all-gather + merge_pairs_kernel"),
+                        "ms_per_step": exc, "share_of_step": exc / ms_per_step, "local_scan_select_ms": loc,
+                        "nvlink_bytes_out_per_rank": (world - 1) * per * k * 12 * 2 if index.exchange == "p2p" else None}
     value = nq / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API with HOST buffers: H2D of the claims, D2H of the result
@@ -544,7 +564,7 @@ def run_b200(args):
     roofline = {"bound": "tensor", "achieved": ach_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": ach_tflops / peaks["tflops"], "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peaks["source"],
-                "kernel": "gemm_nt_tc_kernel<2, TopKEpilogue<16>>" + ("" if prof else " (+ select, adaptive passes)"),
+                "kernel": "gemm_nt_tc_kernel<2, TopKEpilogue<16>>" + ("" if prof else " (+ merge_runs select, adaptive passes)"),
                 "kernel_ms": kern_ms,
                 "hbm_frac": ach_gbs / peaks["hbm_gbs"], "mma_frac": ach_tflops / peaks["tflops"],
                 "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": bytes_alg}
@@ -552,13 +572,16 @@ def run_b200(args):
     # staging + scan + select on one GPU; sharded: staging + scan + the fused select/exchange/merge kernel + its
     # call-counter bump (p2p), or staging + scan + select + merge (nccl)
     launches_per_step = 3 if world == 1 else 4
+    if k > 16:      # adaptive passes: (staging + scan + merge) per enqueued pass (+ 3 memsets), then the exchange + its counter bump
+        launches_per_step = 3 * -(-k // 16) + (2 if world > 1 else 0)
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "claims/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if args.workload == "fever_sentences_25M" else f"claims/sec top-{k} over {nc} x {dim} bf16 corpus", "value": value, "unit": "claims/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {nq} claims x {nc} x {dim} bf16, top-{k}",
-                       "parallelism": (f"corpus row-sharded x{world}, " + ("fused select + NVLink peer-memory exchange + merge kernel"
+                       "parallelism": (f"corpus row-sharded x{world}, " + (("fused select + NVLink peer-memory exchange + merge kernel" if k <= 16 else
+                                                                            "select passes, then the query-sliced NVLink peer-memory exchange + merge kernel")
                                                                            if world > 1 and index.exchange == "p2p" else
                                                                            "NCCL all-gather + on-GPU merge") if world > 1 else "one GPU, whole corpus resident"),
                        "l2": "corpus shard (>= 4.8 GB) exceeds the 126 MB L2 every step; no flush needed",
@@ -566,6 +589,9 @@ def run_b200(args):
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clk.summary(), "roofline": roofline,
             "parity": parity,
         }
+        if exchange_rec:
+            line["exchange"] = exchange_rec
+        line["coop_fallbacks"] = drs_b200.get_option("debug.coop_fallbacks")
         if regimes:
             line["small_batch_regime"] = regimes
             line["small_batch_regime_note"] = (f"hbm_frac = algorithmic bytes / scan time / {peaks['hbm_gbs']:.0f} GB/s, the measured "
