@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -60,9 +61,25 @@ struct Options {
   int round_barrier = 1;
   int seed_thresholds = 1;
   int symmetric_grad = 1;
+  int m_block = 0;         // search: A tiles per super-block of the unit order: 0 auto (= clusters), -1 off
+  int df_tile = 0;         // InfoNCE dF = H F GEMM tile width: 0 auto, 256, 192
+  int fp32_mode = 0;       // DRS_F32 search: 0 = 3 x TF32 on tcgen05 (when dim % 4 == 0 and 16-byte aligned), 1 = FFMA kernel
   int cooperative = 1;     // launch the kernels that spin on grid-wide flags cooperatively (driver-checked co-residency)
   int coop_fallbacks = 0;  // read-only counter: launches that gave up the round barrier (grid not co-resident)
 } g_opt;
+
+// DRS_COOPERATIVE=0/1 overrides "tune.cooperative" from the environment (read once).  Nsight Compute cannot replay a
+// cooperative launch of a clustered kernel on this driver (the profiled process dies at that launch), so when a
+// profiler's injection library is announced in the environment and nothing was said, the attribute is left out: the
+// barrier then relies on the occupancy check alone, as it did before cooperative launches were introduced.
+void init_options_from_env() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  if (const char* v = getenv("DRS_COOPERATIVE")) g_opt.cooperative = atoi(v) != 0;
+  else if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_NSIGHT_INJECTION_PORT_BASE") || getenv("NVTX_INJECTION64_PATH"))
+    g_opt.cooperative = 0;
+}
 
 struct DeviceInfo {
   int device = -1;
@@ -71,6 +88,7 @@ struct DeviceInfo {
 };
 int get_device_info(DeviceInfo* out) {
   static thread_local DeviceInfo cache[64];
+  init_options_from_env();
   int dev = 0;
   DRS_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail(DRS_ERR_INVALID, "device ordinal %d out of range", dev);
@@ -131,6 +149,21 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int dim, int 
   return DRS_OK;
 }
 
+// [rows, dim] fp32 row-major; box = 32 (K, one 128-byte swizzle row) x box_rows
+int make_tmap_f32(CUtensorMap* m, const void* base, int64_t rows, int dim, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(DRS_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim) * 4};
+  cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DRS_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed (CUresult %d)", static_cast<int>(r));
+  return DRS_OK;
+}
+
 // ------------------------------------------------------------------ work decomposition
 // units = num_m_tiles * splits, dealt round-robin to `groups` persistent clusters; a unit is `tiles_per_split`
 // consecutive B tiles against one A tile.
@@ -170,6 +203,7 @@ drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int 
   s.round_counter = nullptr;
   s.active = nullptr;
   s.f16_operands = 0;
+  s.m_block = 0;
   s.skip_below_diagonal = 0;
   return s;
 }
@@ -194,12 +228,16 @@ struct SearchPlan {
   int seed_slots;     // certificates kept per claim: ceil(k / seed_group)
   int seed_group;     // rows certified by one published value (epilogues.cuh)
   int seed_chunks;    // values a unit publishes: seed_chunks * seed_group <= entries selected per pass
+  bool f32_tc;        // DRS_F32 on the tensor cores (3 x TF32): claims and corpus are split into hi + lo first
+  bool f32_prepared;  // the split of this call has been enqueued (multi-pass searches split once)
+  size_t f32_a_bytes; // one padded [a_rows, dim] fp32 copy of the claims (two are kept: hi, lo)
+  size_t f32_b_bytes; // the corpus residual [nc, dim] fp32
   size_t pad_bytes;   // bf16: zero-padded copy of the claims when nq is not a multiple of the A tile (see scan_pass)
   int64_t a_rows;     // rows of the A operand as the tensor map sees it (nq rounded up when padded)
   size_t ws_bytes;
 };
 
-int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p) {
+int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p, bool allow_f32_tc = true) {
   if (nq <= 0 || nc <= 0 || dim <= 0) return fail(DRS_ERR_INVALID, "nq, nc, dim must be positive (got %lld, %lld, %d)", (long long)nq, (long long)nc, dim);
   if (k <= 0 || k > DRS_MAX_K) return fail(DRS_ERR_UNSUPPORTED, "k must be in [1, %d] (got %d)", DRS_MAX_K, k);
   if (nq > 0x7fffffffLL - 512 || nc > 0x7fffffffLL - 512) return fail(DRS_ERR_UNSUPPORTED, "nq and nc must fit in int32 (shard larger corpora)");
@@ -207,9 +245,12 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
   if (int rc = get_device_info(&di)) return rc;
   p->dtype = dtype;
   p->k = k;
-  if (is_16bit(dtype)) {
+  p->f32_tc = dtype == DRS_F32 && allow_f32_tc && g_opt.fp32_mode == 0 && di.cc_major == 10 && dim % 4 == 0;
+  p->f32_prepared = false;
+  p->f32_a_bytes = p->f32_b_bytes = 0;
+  if (is_16bit(dtype) || p->f32_tc) {
     if (di.cc_major != 10) return fail(DRS_ERR_UNSUPPORTED, "the bf16 path needs an sm_100 device (tcgen05/TMEM); this is sm_%d%d", di.cc_major, di.cc_minor);
-    if (dim % 8 != 0) return fail(DRS_ERR_INVALID, "bf16 path: dim must be a multiple of 8 (TMA 16-byte row pitch), got %d", dim);
+    if (is_16bit(dtype) && dim % 8 != 0) return fail(DRS_ERR_INVALID, "bf16 path: dim must be a multiple of 8 (TMA 16-byte row pitch), got %d", dim);
     // CTA pair (256-row A tiles) for large batches; single CTAs (128-row tiles) up to 128 claims, and near the
     // ridge of the two roofs (<= 1024 claims) whenever they pad the batch less: 384 claims are 3 x 128 exactly
     // but 2 x 256 with a quarter of every MMA wasted (15.3 vs 16.9 ms over 25M rows, 3.5 vs 4.4 ms over 6.25M).
@@ -224,8 +265,9 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
     ctas = std::max(cg, ctas - ctas % cg);
     p->cg = cg;
     p->grid = ctas;
-    p->shape = plan_shape(nq, nc, (dim + 63) / 64, 128 * cg, 256, ctas / cg, g_opt.splits, kTcColGroups);
+    p->shape = plan_shape(nq, nc, p->f32_tc ? (dim + 31) / 32 : (dim + 63) / 64, 128 * cg, 256, ctas / cg, g_opt.splits, kTcColGroups);
     p->shape.f16_operands = dtype == DRS_F16;
+    p->shape.m_block = g_opt.m_block < 0 ? 0 : (g_opt.m_block > 0 ? g_opt.m_block : ctas / cg);   // A super-blocks (gemm_tc.cuh::unit_to_tile)
   } else if (dtype == DRS_F32) {
     int ctas = g_opt.num_ctas > 0 ? g_opt.num_ctas : 2 * di.num_sms;
     p->cg = 1;
@@ -250,6 +292,14 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
   p->cand_bytes = align256s(static_cast<size_t>(nq) * num_slots(p->shape) * p->kcap * sizeof(uint64_t));
   p->pad_bytes = 0;
   p->a_rows = nq;
+  if (p->f32_tc) {
+    // the claims are always staged (hi and lo copies, zero-padded to whole A tiles); the corpus keeps its own
+    // words as the hi part and gets a residual array
+    const int64_t tile = 128 * p->cg;
+    p->a_rows = (nq + tile - 1) / tile * tile;
+    p->f32_a_bytes = align256s(static_cast<size_t>(p->a_rows) * dim * 4);
+    p->f32_b_bytes = align256s(static_cast<size_t>(nc) * dim * 4);
+  }
   if (is_16bit(dtype)) {
     // TMA boxes that hang over the end of the claims matrix are zero-filled correctly but SLOWLY (measured:
     // 1 claim in a 128-row box streams the corpus at 4.7 TB/s, the same claim zero-padded in memory at
@@ -267,8 +317,9 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
     p->seed_group = k_pass / p->seed_chunks;
     p->seed_slots = (k + p->seed_group - 1) / p->seed_group;
   }
-  p->seed_bytes = align256s(static_cast<size_t>(nq) * p->seed_slots * sizeof(uint32_t));
-  p->ws_bytes = kWsHeaderBytes + p->bound_bytes + p->cand_bytes + p->pad_bytes + p->seed_bytes;
+  if (p->seed_slots > drs::kMaxSeedSlots) return fail(DRS_ERR_UNSUPPORTED, "internal: %d seed slots exceed the limit", p->seed_slots);
+  p->seed_bytes = align256s(static_cast<size_t>(nq) * (p->seed_slots + 1) * sizeof(uint32_t));   // + the floor word
+  p->ws_bytes = kWsHeaderBytes + p->bound_bytes + p->cand_bytes + p->pad_bytes + p->seed_bytes + 2 * p->f32_a_bytes + p->f32_b_bytes;
   return DRS_OK;
 }
 
@@ -279,15 +330,28 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
 // and carve-outs), and the kernel is launched COOPERATIVELY, so the driver either places the whole grid at once --
 // waiting for a kernel on another stream to leave if it must -- or refuses the launch.  If either check fails the
 // scan runs without the barrier (correct, more DRAM traffic) and `debug.coop_fallbacks` counts it.
-template <int CG, class Epi, int BN = 256>
+// PREC = 1 (fp32 operands as hi + lo, three kind::tf32 MMAs per K step): a / b are the hi parts -- any fp32 matrix,
+// the tensor core reads the top 19 bits of every word -- and a_lo / b_lo the matching residuals (split_f32_kernel).
+template <int CG, class Epi, int BN = 256, int PREC = 0>
 int launch_gemm_tc(const void* a, const void* b, int kdim, drs::GemmShape shp, int grid,
                    const typename Epi::Params& ep, cudaStream_t st, int64_t a_rows_alloc = 0, int64_t pitch_a = 0,
-                   int64_t pitch_b = 0) {
-  using Cfg = drs::GemmCfg<CG, BN>;
-  CUtensorMap ta, tb;
-  if (int rc = make_tmap_bf16(&ta, a, a_rows_alloc > 0 ? a_rows_alloc : shp.rows_a, kdim, Cfg::BM, shp.f16_operands != 0, pitch_a)) return rc;
-  if (int rc = make_tmap_bf16(&tb, b, shp.rows_b, kdim, Cfg::BN_CTA, shp.f16_operands != 0, pitch_b)) return rc;
-  auto kern = drs::gemm_nt_tc_kernel<CG, Epi, BN>;
+                   int64_t pitch_b = 0, const void* a_lo = nullptr, const void* b_lo = nullptr) {
+  using Cfg = drs::GemmCfg<CG, BN, PREC>;
+  CUtensorMap ta, tb, ta_lo, tb_lo;
+  const int64_t rows_a_map = a_rows_alloc > 0 ? a_rows_alloc : shp.rows_a;
+  if constexpr (PREC == 0) {
+    if (int rc = make_tmap_bf16(&ta, a, rows_a_map, kdim, Cfg::BM, shp.f16_operands != 0, pitch_a)) return rc;
+    if (int rc = make_tmap_bf16(&tb, b, shp.rows_b, kdim, Cfg::BN_CTA, shp.f16_operands != 0, pitch_b)) return rc;
+    ta_lo = ta;
+    tb_lo = tb;
+  } else {
+    if (!a_lo || !b_lo) return fail(DRS_ERR_INVALID, "fp32 tensor-core GEMM needs the lo parts of both operands");
+    if (int rc = make_tmap_f32(&ta, a, rows_a_map, kdim, Cfg::BM)) return rc;
+    if (int rc = make_tmap_f32(&tb, b, shp.rows_b, kdim, Cfg::BN_CTA)) return rc;
+    if (int rc = make_tmap_f32(&ta_lo, a_lo, rows_a_map, kdim, Cfg::BM)) return rc;
+    if (int rc = make_tmap_f32(&tb_lo, b_lo, shp.rows_b, kdim, Cfg::BN_CTA)) return rc;
+  }
+  auto kern = drs::gemm_nt_tc_kernel<CG, Epi, BN, PREC>;
   static thread_local bool attr_set[64] = {};
   static thread_local int max_clusters[64] = {};
   int dev = 0;
@@ -325,7 +389,7 @@ int launch_gemm_tc(const void* a, const void* b, int kdim, drs::GemmShape shp, i
       cfg.numAttrs = 2;
     }
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, shp, ep);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, ta_lo, tb_lo, shp, ep);
   if (e != cudaSuccess && cfg.numAttrs == 2 &&
       (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported || e == cudaErrorInvalidValue ||
        e == cudaErrorInvalidConfiguration)) {
@@ -333,16 +397,16 @@ int launch_gemm_tc(const void* a, const void* b, int kdim, drs::GemmShape shp, i
     shp.round_counter = nullptr;
     cfg.numAttrs = 1;
     ++g_opt.coop_fallbacks;
-    e = cudaLaunchKernelEx(&cfg, kern, ta, tb, shp, ep);
+    e = cudaLaunchKernelEx(&cfg, kern, ta, tb, ta_lo, tb_lo, shp, ep);
   }
   DRS_CUDA(e);
   return DRS_OK;
 }
-template <class Epi>
+template <class Epi, int BN = 256>
 int launch_gemm_tc_cg(int cg, const void* a, const void* b, int kdim, const drs::GemmShape& shp, int grid,
                       const typename Epi::Params& ep, cudaStream_t st, int64_t pitch_a = 0, int64_t pitch_b = 0) {
-  return cg == 2 ? launch_gemm_tc<2, Epi>(a, b, kdim, shp, grid, ep, st, 0, pitch_a, pitch_b)
-                 : launch_gemm_tc<1, Epi>(a, b, kdim, shp, grid, ep, st, 0, pitch_a, pitch_b);
+  return cg == 2 ? launch_gemm_tc<2, Epi, BN>(a, b, kdim, shp, grid, ep, st, 0, pitch_a, pitch_b)
+                 : launch_gemm_tc<1, Epi, BN>(a, b, kdim, shp, grid, ep, st, 0, pitch_a, pitch_b);
 }
 template <class Epi, bool B_KN>
 int launch_gemm_simt(const float* a, long long lda, const float* b, long long ldb, int kdim,
@@ -354,17 +418,18 @@ int launch_gemm_simt(const float* a, long long lda, const float* b, long long ld
   return DRS_OK;
 }
 
-template <int CG, int KCAP>
+template <int CG, int KCAP, int PREC = 0>
 int launch_search_tc(const SearchPlan& p, const void* queries, const void* corpus, int dim, uint64_t* ws, int k_pass,
-                     const uint64_t* bound, const float* col_bias, uint32_t* seeds, cudaStream_t st) {
+                     const uint64_t* bound, const float* col_bias, uint32_t* seeds, cudaStream_t st,
+                     const void* queries_lo = nullptr, const void* corpus_lo = nullptr) {
   if (col_bias != nullptr) {
     using Epi = drs::TopKEpilogue<KCAP, true>;
     typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, col_bias, 2.0f, seeds, p.seed_slots, p.seed_group, p.seed_chunks};
-    return launch_gemm_tc<CG, Epi>(queries, corpus, dim, p.shape, p.grid, ep, st, p.a_rows);
+    return launch_gemm_tc<CG, Epi, 256, PREC>(queries, corpus, dim, p.shape, p.grid, ep, st, p.a_rows, 0, 0, queries_lo, corpus_lo);
   }
   using Epi = drs::TopKEpilogue<KCAP>;
   typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, nullptr, 1.0f, seeds, p.seed_slots, p.seed_group, p.seed_chunks};
-  return launch_gemm_tc<CG, Epi>(queries, corpus, dim, p.shape, p.grid, ep, st, p.a_rows);
+  return launch_gemm_tc<CG, Epi, 256, PREC>(queries, corpus, dim, p.shape, p.grid, ep, st, p.a_rows, 0, 0, queries_lo, corpus_lo);
 }
 
 template <int KCAP>
@@ -478,6 +543,7 @@ int drs_debug_max_clusters(int cluster_size, int* out) {
 
 int drs_set_option(const char* name, int value) {
   if (!name) return fail(DRS_ERR_INVALID, "null option name");
+  init_options_from_env();
   if (!strcmp(name, "search.cta_group")) g_opt.cta_group = value;
   else if (!strcmp(name, "search.num_ctas")) g_opt.num_ctas = value;
   else if (!strcmp(name, "search.splits")) g_opt.splits = value;
@@ -489,6 +555,9 @@ int drs_set_option(const char* name, int value) {
   else if (!strcmp(name, "tune.seed_thresholds")) g_opt.seed_thresholds = value;
   else if (!strcmp(name, "tune.symmetric_grad")) g_opt.symmetric_grad = value;
   else if (!strcmp(name, "tune.cooperative")) g_opt.cooperative = value;
+  else if (!strcmp(name, "search.fp32_mode")) g_opt.fp32_mode = value;
+  else if (!strcmp(name, "infonce.df_tile")) g_opt.df_tile = value;
+  else if (!strcmp(name, "search.m_block")) g_opt.m_block = value;
   else if (!strcmp(name, "debug.coop_fallbacks")) g_opt.coop_fallbacks = value;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;
@@ -506,6 +575,9 @@ int drs_get_option(const char* name, int* value) {
   else if (!strcmp(name, "tune.seed_thresholds")) *value = g_opt.seed_thresholds;
   else if (!strcmp(name, "tune.symmetric_grad")) *value = g_opt.symmetric_grad;
   else if (!strcmp(name, "tune.cooperative")) *value = g_opt.cooperative;
+  else if (!strcmp(name, "search.fp32_mode")) *value = g_opt.fp32_mode;
+  else if (!strcmp(name, "infonce.df_tile")) *value = g_opt.df_tile;
+  else if (!strcmp(name, "search.m_block")) *value = g_opt.m_block;
   else if (!strcmp(name, "debug.coop_fallbacks")) *value = g_opt.coop_fallbacks;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;
@@ -530,17 +602,19 @@ int scan_pass(SearchPlan& p, const void* queries, const void* corpus, int dim, v
   // seeds pay only when a claim's units run one after another: with a single round (units <= groups, e.g. one A
   // tile split 148 ways) nobody ever reads them, and 296 lists publishing for the same 128 claims at the same
   // moment contend on the compare-and-swap (measured +100 us on a 370 us scan)
-  const int groups = is_16bit(p.dtype) ? p.grid / p.cg : p.grid;
+  const bool tc = is_16bit(p.dtype) || p.f32_tc;
+  const int groups = tc ? p.grid / p.cg : p.grid;
   if (g_opt.seed_thresholds && p.shape.num_splits > 1 && p.shape.num_m_tiles * p.shape.num_splits > groups)
     seeds = reinterpret_cast<uint32_t*>(base + kWsHeaderBytes + p.bound_bytes + extra_bytes + p.cand_bytes + p.pad_bytes);
   uint64_t* ws = reinterpret_cast<uint64_t*>(base + kWsHeaderBytes + p.bound_bytes + extra_bytes);
   p.shape.round_counter = nullptr;
   char* pad = nullptr;
-  if (is_16bit(p.dtype)) {
+  if (tc) {
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
-    // requested here, granted by launch_gemm_tc only if the whole grid is co-resident (occupancy query + cooperative launch)
-    if (g_opt.round_barrier && p.grid <= di.num_sms)
+    // requested here -- only when some cluster runs more than one unit, else nobody would ever wait on it -- and
+    // granted by launch_gemm_tc only if the whole grid is co-resident (occupancy query + cooperative launch)
+    if (g_opt.round_barrier && p.grid <= di.num_sms && p.shape.num_m_tiles * p.shape.num_splits > groups)
       p.shape.round_counter = static_cast<unsigned int*>(workspace);
     if (p.pad_bytes) pad = reinterpret_cast<char*>(ws) + p.cand_bytes;  // zero-padded claims (plan_search explains why)
   }
@@ -557,6 +631,27 @@ int scan_pass(SearchPlan& p, const void* queries, const void* corpus, int dim, v
     DRS_CUDA(cudaGetLastError());
     if (pad) queries = pad;
   }
+  if (p.f32_tc) {
+    // operands as hi + lo: [.. seeds | claims hi | claims lo | corpus lo]; split once per call (every pass reuses it)
+    char* f32 = reinterpret_cast<char*>(ws) + p.cand_bytes + p.pad_bytes + p.seed_bytes;
+    float* a_hi = reinterpret_cast<float*>(f32);
+    float* a_lo = reinterpret_cast<float*>(f32 + p.f32_a_bytes);
+    float* b_lo = reinterpret_cast<float*>(f32 + 2 * p.f32_a_bytes);
+    if (!p.f32_prepared) {
+      const size_t na = static_cast<size_t>(p.a_rows) * dim, live = static_cast<size_t>(p.shape.rows_a) * dim;
+      const size_t nb = static_cast<size_t>(p.shape.rows_b) * dim;
+      drs::split_f32_kernel<<<static_cast<int>(std::min<size_t>((na / 4 + 255) / 256, 4096)), 256, 0, st>>>(
+          static_cast<const float4*>(queries), live / 4, na / 4, reinterpret_cast<float4*>(a_hi), reinterpret_cast<float4*>(a_lo));
+      drs::split_f32_kernel<<<static_cast<int>(std::min<size_t>((nb / 4 + 255) / 256, 8192)), 256, 0, st>>>(
+          static_cast<const float4*>(corpus), nb / 4, nb / 4, nullptr, reinterpret_cast<float4*>(b_lo));
+      DRS_CUDA(cudaGetLastError());
+      p.f32_prepared = true;
+    }
+#define DRS_F32TC(CGV, KC) launch_search_tc<CGV, KC, 1>(p, a_hi, corpus, dim, ws, k_pass, bound, col_bias, seeds, st, a_lo, b_lo)
+    if (p.cg == 1) return p.kcap == 16 ? DRS_F32TC(1, 16) : DRS_F32TC(1, 32);
+    return p.kcap == 16 ? DRS_F32TC(2, 16) : DRS_F32TC(2, 32);
+#undef DRS_F32TC
+  }
   if (is_16bit(p.dtype)) {
     if (p.cg == 1) return p.kcap == 16 ? launch_search_tc<1, 16>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, seeds, st)
                                        : launch_search_tc<1, 32>(p, queries, corpus, dim, ws, k_pass, bound, col_bias, seeds, st);
@@ -572,8 +667,8 @@ int check_search_args(const SearchPlan& p, const void* queries, const void* corp
   if (!workspace || workspace_bytes < p.ws_bytes)
     return fail(DRS_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", p.ws_bytes, workspace_bytes);
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(DRS_ERR_INVALID, "workspace must be 256-byte aligned");
-  if (is_16bit(p.dtype) && ((reinterpret_cast<uintptr_t>(queries) & 15) || (reinterpret_cast<uintptr_t>(corpus) & 15)))
-    return fail(DRS_ERR_INVALID, "bf16 path: queries and corpus must be 16-byte aligned");
+  if ((is_16bit(p.dtype) || p.f32_tc) && ((reinterpret_cast<uintptr_t>(queries) & 15) || (reinterpret_cast<uintptr_t>(corpus) & 15)))
+    return fail(DRS_ERR_INVALID, "tensor-core path: queries and corpus must be 16-byte aligned");
   return DRS_OK;
 }
 }  // namespace

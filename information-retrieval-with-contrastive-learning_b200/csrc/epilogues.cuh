@@ -12,6 +12,8 @@ namespace drs {
 // TfidfDocRanker.closest_docs (preprocessing/drqa/retriever/tfidf_doc_ranker.py:67-73) for the
 // dense scores of src/evaluation.py:110-115.  Output: KCAP packed keys per (claim, split) in the
 // workspace; merge.cuh reduces the splits to the final k.
+constexpr int kMaxSeedSlots = 96;   // >= ceil(DRS_MAX_K / 3): certificates kept per claim (plan_search)
+
 template <int KCAP, bool BIASED = false>
 struct TopKEpilogue {
   struct Params {
@@ -24,16 +26,20 @@ struct TopKEpilogue {
                             // (k > KCAP is served in passes: each pass continues below the last pick)
     const float* col_bias;  // BIASED: ranked value = score_scale * dot + col_bias[col]
     float score_scale;      //   (squared-L2 search: 2 x.c - |c|^2, src/contrastor/utils.py:64-67)
-    // Threshold seeding across units.  seeds: [rows_a][seed_slots] ordered-uint32 scores, zeroed before the
-    // scan.  A unit's sorted list is cut into seed_chunks groups of seed_group entries; group c's smallest
-    // entry v_c = sc[c * seed_group - 1] certifies seed_group rows of the unit's corpus range that score
-    // >= v_c, disjoint from every other group of every unit.  Each claim keeps the seed_slots largest
-    // certificates published so far (replace-the-minimum by compare-and-swap); with seed_slots * seed_group >=
-    // (the k the caller wants) their minimum is a lower bound on the final k-th best score.  Later units of the
-    // claim start from it instead of from -inf and stay on the fast path (a fresh list needs ~k ln(n/k) inserts
-    // to warm up, and one lane's insert stalls its warp).  Every certified row is in a candidate list, so
-    // the select still sees >= k rows at or above the bound; stale or missing seeds only weaken it -- the
-    // result is exact either way.
+    // Threshold seeding across units.  seeds: [rows_a][1 + seed_slots] ordered-uint32 scores, zeroed before the
+    // scan: word 0 is the claim's current FLOOR, words 1.. are certificates.  A unit's sorted list is cut into
+    // seed_chunks groups of seed_group entries; group c's smallest entry v_c = sc[c * seed_group - 1] certifies
+    // seed_group rows of the unit's corpus range that score >= v_c, disjoint from every other group of every unit.
+    // Each claim keeps the seed_slots largest certificates published so far (replace-the-minimum by
+    // compare-and-swap); with seed_slots * seed_group >= (the k the caller wants) their minimum is a lower bound on
+    // the final k-th best score, published with atomicMax into the floor word.  Later units of the claim start
+    // from it instead of from -inf and stay on the fast path (a fresh list needs ~k ln(n/k) inserts to warm up, and
+    // one lane's insert stalls its warp).  Every certified row is in a candidate list, so the select still sees >= k
+    // rows at or above the bound; stale or missing seeds only weaken it -- the result is exact either way.
+    // Cost per unit: ONE load at the start; at the end one batch of independent loads (the certificates), the
+    // replace-the-minimum bookkeeping on a private copy, and up to seed_chunks fire-and-forget CAS + one atomicMax.
+    // (The first version walked the slots with dependent L2 round trips -- 34 slots x 5 certificates for top-100 --
+    // and that walk, at every unit end, was what held the top-100 scan at 73 % tensor-pipe activity.)
     uint32_t* seeds;
     int seed_slots;
     int seed_group;
@@ -49,16 +55,7 @@ struct TopKEpilogue {
     if (bnd == 0ull) {
       floor = INFINITY;  // this claim is complete: nothing is eligible, stay on the fast path
     } else if (p.seeds != nullptr && row < p.rows_a) {
-      // four independent L2 loads in flight per step (a serial chain of up to 86 L2 round trips at every unit
-      // start showed up in the ncu samples)
-      const uint32_t* a = p.seeds + static_cast<size_t>(row) * p.seed_slots;
-      uint32_t lo = 0xFFFFFFFFu;
-      int j = 0;
-      for (; j + 3 < p.seed_slots; j += 4) {
-        const uint32_t x0 = __ldcg(a + j), x1 = __ldcg(a + j + 1), x2 = __ldcg(a + j + 2), x3 = __ldcg(a + j + 3);
-        lo = min(lo, min(min(x0, x1), min(x2, x3)));
-      }
-      for (; j < p.seed_slots; ++j) lo = min(lo, __ldcg(a + j));
+      const uint32_t lo = __ldcg(p.seeds + static_cast<size_t>(row) * (p.seed_slots + 1));
       // strictly below the bound, so that rows TYING it (with a lower index) still enter.  The predecessor of
       // +0.0 in the ordered domain decodes to -0.0, which `s > thr` cannot tell from +0.0: step once more
       // (to the largest negative float), or rows scoring exactly 0 -- zero-padded corpus rows, all-zero
@@ -126,25 +123,44 @@ struct TopKEpilogue {
 #pragma unroll
     for (int j = 0; j < KCAP; ++j) dst[j] = list.key(j);
     if (p.seeds != nullptr) {
-      uint32_t* a = p.seeds + static_cast<size_t>(row) * p.seed_slots;
-      for (int c = 1; c <= p.seed_chunks; ++c) {          // best group first: each success raises the minimum
+      uint32_t* a = p.seeds + static_cast<size_t>(row) * (p.seed_slots + 1);
+      uint32_t cert[5];                                   // this unit's certificates, best first (seed_chunks <= 5)
+      int ncert = 0;
+#pragma unroll
+      for (int c = 1; c <= 5; ++c) {
         const int pos = c * p.seed_group - 1;
         float val = -INFINITY;
 #pragma unroll
         for (int j = 0; j < KCAP; ++j) val = (j == pos) ? list.sc[j] : val;
-        if (!(val > list.floor)) break;                   // empty, or below what the claim already had at the start
-        const uint32_t v = float_to_ordered(val);
-        for (;;) {
-          uint32_t mn = 0xFFFFFFFFu;
-          int mi = 0;
-          for (int j = 0; j < p.seed_slots; ++j) {
-            const uint32_t x = __ldcg(a + j);
-            if (x < mn) { mn = x; mi = j; }
-          }
-          if (v <= mn) break;                             // not among the seed_slots largest
-          if (atomicCAS(a + mi, mn, v) == mn) break;      // replaced the minimum; else someone else moved it: retry
-        }
+        // empty, or not above what the claim already had when the unit started: nothing to add (values descend)
+        const bool live = c <= p.seed_chunks && val > list.floor && ncert == c - 1;
+        cert[c - 1] = live ? float_to_ordered(val) : 0u;
+        ncert += live ? 1 : 0;
       }
+      if (ncert == 0) return;
+      uint32_t sl[kMaxSeedSlots];                         // private copy of the claim's certificates
+      for (int j = 0; j < p.seed_slots; j += 8) {         // independent loads: one L2 round trip per 8 slots
+        uint32_t x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = (j + i < p.seed_slots) ? __ldcg(a + 1 + j + i) : 0xFFFFFFFFu;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (j + i < p.seed_slots) sl[j + i] = x[i];
+      }
+      for (int c = 0; c < ncert; ++c) {
+        uint32_t mn = 0xFFFFFFFFu;
+        int mi = 0;
+        for (int j = 0; j < p.seed_slots; ++j)
+          if (sl[j] < mn) { mn = sl[j]; mi = j; }
+        if (cert[c] <= mn) break;                         // not among the seed_slots largest (nor are the smaller ones)
+        // fire and forget: a lost race only drops this certificate from the shared array (a weaker bound for
+        // others); the private copy stays a set of valid, disjoint certificates either way
+        atomicCAS(a + 1 + mi, mn, cert[c]);
+        sl[mi] = cert[c];
+      }
+      uint32_t mn = 0xFFFFFFFFu;
+      for (int j = 0; j < p.seed_slots; ++j) mn = min(mn, sl[j]);
+      if (mn != 0u) atomicMax(a, mn);                     // all slots filled: their minimum bounds the k-th best
     }
   }
 };

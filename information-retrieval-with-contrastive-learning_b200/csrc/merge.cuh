@@ -142,17 +142,21 @@ merge_runs_kernel(const uint64_t* __restrict__ ws, int nq, int nslots, int kcap,
   if (q >= nq) return;
   int r = done[q];
   if (r >= k) return;
+  uint64_t keep = 0ull;
+  const int r_begin = r;        // picks before this one were emitted by earlier passes
   const uint64_t* src = ws + static_cast<size_t>(q) * nslots * kcap;
-  uint64_t head[SL];
-  int pos[SL];
+  uint64_t head[SL], nxt[SL];   // nxt: the run's following key, loaded when the head is taken -- the pick loop
+  int pos[SL];                  // never waits on memory (a dependent L2 load per pick made this kernel 1.1 ms)
   uint64_t hidden = 0ull;  // B
 #pragma unroll
   for (int i = 0; i < SL; ++i) {
     const int slot = lane + 32 * i;
     pos[i] = 0;
     head[i] = 0ull;
+    nxt[i] = 0ull;
     if (slot < nslots) {
       head[i] = src[static_cast<size_t>(slot) * kcap];
+      nxt[i] = kcap > 1 ? src[static_cast<size_t>(slot) * kcap + 1] : 0ull;
       const uint64_t last = src[static_cast<size_t>(slot) * kcap + kcap - 1];
       hidden = last > hidden ? last : hidden;
     }
@@ -172,17 +176,34 @@ merge_runs_kernel(const uint64_t* __restrict__ ws, int nq, int nslots, int kcap,
       for (int i = 0; i < SL; ++i) {
         if (head[i] == best) {
           ++pos[i];
-          head[i] = pos[i] < kcap ? src[static_cast<size_t>(lane + 32 * i) * kcap + pos[i]] : 0ull;
+          head[i] = nxt[i];
+          nxt[i] = pos[i] + 1 < kcap ? src[static_cast<size_t>(lane + 32 * i) * kcap + pos[i] + 1] : 0ull;
         }
       }
     }
-    if (lane == 0) {
-      float sc = key_score(best);
-      if (row_term != nullptr) sc = fmaxf(row_term[q] - sc, 0.f);
-      out_scores[static_cast<size_t>(q) * ld_out + r] = sc;
-      out_ids[static_cast<size_t>(q) * ld_out + r] = static_cast<long long>(key_index(best)) + id_base;
+    if (lane == (r & 31)) {    // pick r waits in lane r % 32 for a coalesced store
+      keep = best;
+    }
+    if ((r & 31) == 31 || r == k - 1) {
+      const int r0 = r & ~31;
+      if (r0 + lane <= r && r0 + lane >= r_begin) {
+        float sc = key_score(keep);
+        if (row_term != nullptr) sc = fmaxf(row_term[q] - sc, 0.f);
+        out_scores[static_cast<size_t>(q) * ld_out + r0 + lane] = sc;
+        out_ids[static_cast<size_t>(q) * ld_out + r0 + lane] = static_cast<long long>(key_index(keep)) + id_base;
+      }
     }
     prev = best;
+  }
+  // picks of an incomplete group of 32 (the loop stopped early)
+  if (r < k && (r & 31) != 0) {
+    const int r0 = r & ~31;
+    if (r0 + lane < r && r0 + lane >= r_begin) {
+      float sc = key_score(keep);
+      if (row_term != nullptr) sc = fmaxf(row_term[q] - sc, 0.f);
+      out_scores[static_cast<size_t>(q) * ld_out + r0 + lane] = sc;
+      out_ids[static_cast<size_t>(q) * ld_out + r0 + lane] = static_cast<long long>(key_index(keep)) + id_base;
+    }
   }
   if (exhausted) {  // fewer than k rows exist: pad like the single-pass select
     for (int rr = r + lane; rr < k; rr += 32) {
@@ -260,6 +281,24 @@ scan_prep_kernel(uint4* __restrict__ round_counter, uint4* __restrict__ seeds, s
   if (round_counter != nullptr && tid < 16) round_counter[tid] = zero;  // 256 bytes
   for (size_t i = tid; i < seed_vec; i += stride) seeds[i] = zero;
   for (size_t i = tid; i < pad_vec; i += stride) pad[i] = i < live_vec ? claims[i] : zero;
+}
+
+// fp32 -> (hi, lo) for the 3 x TF32 GEMM (gemm_tc.cuh, PREC = 1): hi = x with the 13 low mantissa bits cleared -- the
+// part of the word a kind::tf32 MMA reads -- and lo = x - hi, exact in fp32.  Vectors [live, total) are zero (row
+// padding of the claims).  hi may be null: the caller then feeds the original words as the hi operand.
+__global__ void __launch_bounds__(256)
+split_f32_kernel(const float4* __restrict__ src, size_t live_vec, size_t total_vec, float4* __restrict__ hi, float4* __restrict__ lo) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total_vec; i += stride) {
+    const float4 x = i < live_vec ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 h;
+    h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+    h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+    h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+    h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+    if (hi != nullptr) hi[i] = h;
+    lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+  }
 }
 
 // |row|^2 in fp32 for fp32 or bf16 rows; out[r] = sign * |row|^2.  One warp per row.
