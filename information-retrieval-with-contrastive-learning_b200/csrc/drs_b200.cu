@@ -60,7 +60,7 @@ struct Options {
   int stagger_cycles = 0;
   int round_barrier = 1;
   int seed_thresholds = 1;
-  int symmetric_grad = 1;
+  int symmetric_grad = 2;   // InfoNCE backward: 0 full H, 1 upper tiles computed + mirrored stores, 2 upper tiles only (dF reads transposed)
   int m_block = 0;         // search: A tiles per super-block of the unit order: 0 auto (= clusters), -1 off
   int df_tile = 0;         // InfoNCE dF = H F GEMM tile width: 0 auto, 256, 192
   int fp32_mode = 0;       // DRS_F32 search: 0 = 3 x TF32 on tcgen05 (when dim % 4 == 0 and 16-byte aligned), 1 = FFMA kernel
@@ -204,6 +204,7 @@ drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int 
   s.active = nullptr;
   s.f16_operands = 0;
   s.m_block = 0;
+  s.a_sym = 0;
   s.skip_below_diagonal = 0;
   return s;
 }
@@ -344,6 +345,10 @@ int launch_gemm_tc(const void* a, const void* b, int kdim, drs::GemmShape shp, i
     if (int rc = make_tmap_bf16(&tb, b, shp.rows_b, kdim, Cfg::BN_CTA, shp.f16_operands != 0, pitch_b)) return rc;
     ta_lo = ta;
     tb_lo = tb;
+    if (shp.a_sym) {   // the transposed view of the (square, symmetric) A operand: 64 x 64 boxes of the same matrix
+      if (CG != 2 || shp.rows_a != kdim) return fail(DRS_ERR_INVALID, "internal: a_sym needs the CTA-pair kernel and a square A");
+      if (int rc = make_tmap_bf16(&ta_lo, a, rows_a_map, kdim, 64, shp.f16_operands != 0, pitch_a)) return rc;
+    }
   } else {
     if (!a_lo || !b_lo) return fail(DRS_ERR_INVALID, "fp32 tensor-core GEMM needs the lo parts of both operands");
     if (int rc = make_tmap_f32(&ta, a, rows_a_map, kdim, Cfg::BM)) return rc;

@@ -33,12 +33,17 @@ struct GemmShape {
   int tiles_per_split;  // 256-row B tiles per split
   int total_b_tiles;    // ceil(rows_b / 256)
   int col_groups;       // epilogue threads per A row (each owns a column group of every tile)
-  int debug_flags;      // tuning instrumentation: 1 skip epilogue functor, 2 skip TMEM loads, 4 skip MMA issue
+  int debug_flags;      // tuning instrumentation: 1 skip epilogue functor, 2 skip TMEM loads
   int b_hint;           // L2 eviction hint for the B (corpus) tiles: 0 normal, 1 evict-first, 2 evict-last
   int stagger_cycles;   // producer start delay per A-tile index (experiment knob)
   unsigned int* round_counter;  // zeroed device counter for the per-round producer barrier, or nullptr
   const unsigned int* active;   // optional: the whole launch is a no-op when *active == 0 (adaptive k > 32 passes)
   int f16_operands;             // 0: bf16 operands, 1: IEEE half operands (same kind::f16 MMA, other instruction descriptor)
+  int a_sym;                    // CG == 2, PREC == 0: A is a SYMMETRIC square matrix of which only the 256 x 256 tiles on and
+                                // above the diagonal are stored (the gradient-of-logits matrix H of the InfoNCE backward):
+                                // K blocks left of A tile m's diagonal tile (kb < 4 m) are read TRANSPOSED from the stored
+                                // tile (kb / 4, m) -- two 64 x 64 boxes through `tmap_a_lo` (the same matrix, box 64 x 64),
+                                // laid out as an MN-major operand, and the MMA is told so (descriptor + instruction bit)
   int m_block;                  // > 0 and < num_m_tiles: units are ordered A-super-block by A-super-block (unit_to_tile)
   int skip_below_diagonal;      // A == B, square (A tile rows == B tile rows), symmetric output: only the tiles on and
                                 // above the diagonal are computed, dealt to the clusters as contiguous pieces of the
@@ -194,22 +199,21 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
+  const uint32_t tmem_base = *tmem_ptr_smem;   // (written before the barrier above; a plain load keeps it warp-uniform)
 
   if (warp == kWarpTma) {
-    // ------------------------------------------------------------ TMA producer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    // The WHOLE warp walks the pipeline state and one elected lane issues (elect.sync): with a `lane == 0` branch
+    // around the loop the compiler cannot prove the operands warp-uniform and wraps every TMA / MMA instruction in
+    // an ELECT + 5 x R2UR.BROADCAST + branch "waterfall"; the MMA thread then needs ~300 of the 512 cycles a K block's
+    // four MMAs take just to issue them, and any extra instruction on that path shows up as tensor-pipe idle time.
+    {
       uint32_t stage = 0, phase = 0;
       const uint64_t hint_b = shp.b_hint == 1 ? kEvictFirst : (shp.b_hint == 2 ? kEvictLast : kEvictNormal);
       if (shp.stagger_cycles > 0) {
         const long long until = clock64() + static_cast<long long>(shp.stagger_cycles) * (cluster % shp.num_m_tiles);
         while (clock64() < until) {}
       }
-      // Round barrier: every producer starts round r (its r-th unit) only after ALL producers have
-      // issued the loads of round r-1.  The clusters that share a B range then sweep it in lockstep
-      // and each B tile is fetched from HBM once per round instead of once per straggler (without
-      // it the groups drift apart by more than the L2 can hold and the corpus is re-read ~18x).
-      // All CTAs are co-resident (grid <= SM count, one CTA per SM), so the spin cannot deadlock.
       auto load_tile = [&](int m, int t) {
         const int row_a = (m * CG + static_cast<int>(cta_rank)) * Cfg::BM;
         const int row_b = t * Cfg::BN + static_cast<int>(cta_rank) * Cfg::BN_CTA;
@@ -217,27 +221,42 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           mbar_wait(&empty_bar[stage], phase ^ 1u, kTagProducerEmpty, stage);
           uint8_t* dst_a = smem_a + stage * Cfg::PARTS * Cfg::A_BYTES;
           uint8_t* dst_b = smem_b + stage * Cfg::PARTS * Cfg::B_BYTES;
-          if constexpr (CG == 1) {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_2d(dst_a, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
-            tma_load_2d(dst_b, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, hint_b);
-            if constexpr (PREC == 1) {
-              tma_load_2d(dst_a + Cfg::A_BYTES, &tmap_a_lo, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
-              tma_load_2d(dst_b + Cfg::B_BYTES, &tmap_b_lo, &full_bar[stage], kb * Cfg::BK, row_b, hint_b);
+          const bool a_transposed = CG == 2 && PREC == 0 && shp.a_sym && kb < 4 * m;
+          if (elect_one_sync()) {
+            if constexpr (CG == 1) {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              tma_load_2d(dst_a, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
+              tma_load_2d(dst_b, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, hint_b);
+              if constexpr (PREC == 1) {
+                tma_load_2d(dst_a + Cfg::A_BYTES, &tmap_a_lo, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
+                tma_load_2d(dst_b + Cfg::B_BYTES, &tmap_b_lo, &full_bar[stage], kb * Cfg::BK, row_b, hint_b);
+              }
+            } else {
+              if (a_transposed) {
+                // A[row_a + i][kb * 64 + j] = H[kb * 64 + j][row_a + i]: rows = K, 64 M-elements (128 bytes) per row
+                tma_load_2d_pair(dst_a, &tmap_a_lo, &full_bar[stage], row_a, kb * Cfg::BK, kEvictLast);
+                tma_load_2d_pair(dst_a + 8192, &tmap_a_lo, &full_bar[stage], row_a + 64, kb * Cfg::BK, kEvictLast);
+              } else {
+                tma_load_2d_pair(dst_a, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
+              }
+              tma_load_2d_pair(dst_b, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, hint_b);
+              if constexpr (PREC == 1) {
+                tma_load_2d_pair(dst_a + Cfg::A_BYTES, &tmap_a_lo, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
+                tma_load_2d_pair(dst_b + Cfg::B_BYTES, &tmap_b_lo, &full_bar[stage], kb * Cfg::BK, row_b, hint_b);
+              }
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              else mbar_arrive_cluster(&full_bar[stage], 0);
             }
-          } else {
-            tma_load_2d_pair(dst_a, &tmap_a, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
-            tma_load_2d_pair(dst_b, &tmap_b, &full_bar[stage], kb * Cfg::BK, row_b, hint_b);
-            if constexpr (PREC == 1) {
-              tma_load_2d_pair(dst_a + Cfg::A_BYTES, &tmap_a_lo, &full_bar[stage], kb * Cfg::BK, row_a, kEvictLast);
-              tma_load_2d_pair(dst_b + Cfg::B_BYTES, &tmap_b_lo, &full_bar[stage], kb * Cfg::BK, row_b, hint_b);
-            }
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-            else mbar_arrive_cluster(&full_bar[stage], 0);
           }
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       };
+      // Round barrier: every producer starts round r (its r-th unit) only after ALL producers have
+      // issued the loads of round r-1.  The clusters that share a B range then sweep it in lockstep
+      // and each B tile is fetched from HBM once per round instead of once per straggler (without
+      // it the groups drift apart by more than the L2 can hold and the corpus is re-read ~18x).
+      // Every CTA of the grid is resident (checked and enforced by the launcher), so the spin cannot deadlock.
       if (shp.skip_below_diagonal) {
         for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters); w.valid(); w.next()) load_tile(w.m, w.t);
       } else {
@@ -249,7 +268,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const long long t_start = clock64();
             while (ld_acquire_gpu_u32(shp.round_counter) < target) {
               __nanosleep(64);
-              if (clock64() - t_start > kMbarTimeoutCycles) mbar_hang(kTagRoundBarrier, round, target);
+              if (clock64() - t_start > 10 * kMbarTimeoutCycles) mbar_hang(kTagRoundBarrier, round, target);
             }
           }
           if (u < num_units) {
@@ -259,17 +278,21 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
             for (int t = t0; t < t1; ++t) load_tile(m, t);
           }
-          if (shp.round_counter != nullptr) red_release_gpu_add_u32(shp.round_counter, 1u);
+          if (shp.round_counter != nullptr) {
+            if (elect_one_sync()) red_release_gpu_add_u32(shp.round_counter, 1u);
+            __syncwarp();
+          }
         }
       }
     }
   } else if (warp == kWarpMma) {
-    // ------------------------------------------------------------ MMA issuer (one thread, leader CTA)
-    if (lane == 0 && leader) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA; whole warp, one elected lane issues)
+    if (leader) {
       const uint32_t idesc = PREC == 1 ? make_idesc_tf32_f32(128 * CG, Cfg::BN)
                              : (shp.f16_operands ? make_idesc_f16_f32(128 * CG, Cfg::BN) : make_idesc_bf16_f32(128 * CG, Cfg::BN));
+      const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
       uint32_t stage = 0, phase = 0, it = 0;
-      auto mma_tile = [&]() {
+      auto mma_tile = [&](int m = 0) {
         const uint32_t acc = it % Cfg::ACC_STAGES, acc_phase = (it / Cfg::ACC_STAGES) & 1u;
         ++it;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, kTagMmaTmemEmpty, acc);
@@ -278,25 +301,39 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase, kTagMmaFull, stage);
           tc_fence_after();
-          const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::PARTS * Cfg::A_BYTES));
-          const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::PARTS * Cfg::B_BYTES));
-          if (!(shp.debug_flags & 4)) {
+          const uint32_t a_addr = a_base + stage * (Cfg::PARTS * Cfg::A_BYTES);
+          const uint32_t b_addr = b_base + stage * (Cfg::PARTS * Cfg::B_BYTES);
+          const uint64_t b_desc = make_sw128_kmajor_desc(b_addr);
+          const bool a_transposed = CG == 2 && PREC == 0 && shp.a_sym && kb < 4 * m;
+          if (elect_one_sync()) {
+            if constexpr (PREC == 0) {
+              if (a_transposed) {
+                // MN-major A: 16 K-rows of 128 bytes per instruction = +2048 bytes; M atoms 8192 bytes apart
+                const uint64_t a_mn = make_sw128_mnmajor_desc(a_addr, 8192u, 1024u);
 #pragma unroll
-            for (int k = 0; k < Cfg::BK / Cfg::KSTEP; ++k) {
-              // +32 bytes (16 bf16 / 8 fp32) along K inside the 128-byte swizzle row: start address field += 2
-              if constexpr (PREC == 0) {
-                umma_bf16<CG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < Cfg::BK / Cfg::KSTEP; ++k)
+                  umma_bf16<CG>(d_tmem, a_mn + 128u * k, b_desc + 2u * k, idesc | kIdescAMajorMN, (kb | k) != 0 ? 1u : 0u);
               } else {
-                const uint64_t a_lo = a_desc + (Cfg::A_BYTES >> 4), b_lo = b_desc + (Cfg::B_BYTES >> 4);
-                const uint32_t d_corr = d_tmem + Cfg::BN;                                                  // second accumulator
+                const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
+#pragma unroll
+                for (int k = 0; k < Cfg::BK / Cfg::KSTEP; ++k)   // +32 bytes (16 bf16) along K inside the 128-byte swizzle row
+                  umma_bf16<CG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            } else {
+              const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
+              const uint64_t a_lo = a_desc + (Cfg::A_BYTES >> 4), b_lo = b_desc + (Cfg::B_BYTES >> 4);
+              const uint32_t d_corr = d_tmem + Cfg::BN;                                                  // second accumulator
+#pragma unroll
+              for (int k = 0; k < Cfg::BK / Cfg::KSTEP; ++k) {
                 umma_tf32<CG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);   // hi . hi
                 umma_tf32<CG>(d_corr, a_desc + 2u * k, b_lo + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);     // hi . lo
                 umma_tf32<CG>(d_corr, a_lo + 2u * k, b_desc + 2u * k, idesc, 1u);                          // lo . hi
               }
             }
+            umma_commit<CG>(&empty_bar[stage]);                       // smem slot free once these MMAs retire
+            if (kb == nkb - 1) umma_commit<CG>(&tmem_full_bar[acc]);  // accumulator complete
           }
-          umma_commit<CG>(&empty_bar[stage]);                       // smem slot free once these MMAs retire
-          if (kb == nkb - 1) umma_commit<CG>(&tmem_full_bar[acc]);  // accumulator complete
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       };
@@ -308,7 +345,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           unit_to_tile(shp, u, m, s);
           const int t0 = s * shp.tiles_per_split;
           const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
-          for (int t = t0; t < t1; ++t) mma_tile();
+          for (int t = t0; t < t1; ++t) mma_tile(m);
         }
       }
     }

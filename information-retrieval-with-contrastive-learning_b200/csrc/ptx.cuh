@@ -45,6 +45,17 @@ __device__ __forceinline__ uint32_t num_clusters_x() {
   asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
   return r;
 }
+// One lane of the (converged) warp gets `true`.  Code predicated on it is what the compiler recognises as "issued by
+// a single elected thread": the operands of the TMA / tcgen05 instructions inside stay in uniform registers.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -187,6 +198,15 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>(1024u >> 4) << 32) |
          (1ull << 46) | (2ull << 61);
 }
+// Same for an MN-major operand (the M or N index is the contiguous one): the tile is stored as K rows of 64
+// elements (128 bytes, swizzled like above); 8 K rows form a 1024-byte atom.
+//   [16,30) leading-dim byte offset >> 4 = distance between 64-element atoms along M/N
+//   [32,46) stride byte offset >> 4      = distance between 8-row atoms along K
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
+         (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+static constexpr uint32_t kIdescAMajorMN = 1u << 15;   // instruction descriptor: A operand is MN-major
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major.
 //   [4,6) D format 1=f32   [7,10) A format 1=bf16   [10,13) B format 1=bf16
 //   [15] A major 0=K  [16] B major 0=K   [17,23) N>>3   [24,29) M>>4

@@ -202,25 +202,33 @@ def test_nceloss_with_cluster_result_adds_proto_loss():
     assert (qd.grad.cpu().double() - rdq).abs().max().item() <= 1e-4 * rdq.abs().max().item()
 
 
-def test_symmetric_gradient_matrix_matches_the_full_computation():
-    """Backward at whole 256-row tiles computes only the blocks of H = dL/dS on and above the diagonal and writes
-    each twice (itself and its transpose); the gradients must equal the full computation and the oracle."""
-    n, dim = 1024, 128
+@pytest.mark.parametrize("n,dim", [(1024, 128), (512, 768), (2048, 64)])
+def test_symmetric_gradient_matrix_matches_the_full_computation(n, dim):
+    """Backward at whole 256-row tiles computes only the blocks of H = dL/dS on and above the diagonal.  Mode 2 (default)
+    stores them once and the dF = H F GEMM reads the blocks below the diagonal TRANSPOSED out of the stored ones
+    (MN-major tcgen05 operand); mode 1 writes every block twice (itself and its transpose); mode 0 computes all of H.
+    All three must give the same gradients (same bf16 H values, same accumulation order) and match the oracle."""
     g = torch.Generator().manual_seed(5)
     q = torch.nn.functional.normalize(torch.randn(n, dim, generator=g), dim=1)
     k = torch.nn.functional.normalize(torch.randn(n, dim, generator=g) * 0.5 + q, dim=1)
-    loss1, dq1, dk1 = _run(q, k, None, 0.05, "bf16")
+    res = {}
     try:
-        drs_b200.set_option("tune.symmetric_grad", 0)
-        loss0, dq0, dk0 = _run(q, k, None, 0.05, "bf16")
+        for mode in (2, 1, 0):
+            drs_b200.set_option("tune.symmetric_grad", mode)
+            res[mode] = _run(q, k, None, 0.05, "bf16")
     finally:
-        drs_b200.set_option("tune.symmetric_grad", 1)
-    assert loss1.item() == loss0.item()
+        drs_b200.set_option("tune.symmetric_grad", 2)
+    loss0, dq0, dk0 = res[0]
     scale = dq0.abs().max().item()
-    assert (dq1 - dq0).abs().max().item() <= 1e-6 * scale and (dk1 - dk0).abs().max().item() <= 1e-6 * scale
+    for mode in (1, 2):
+        loss, dq, dk = res[mode]
+        assert loss.item() == loss0.item()
+        assert (dq - dq0).abs().max().item() <= 1e-6 * scale and (dk - dk0).abs().max().item() <= 1e-6 * scale, mode
     rl, rdq, rdk = infonce.nce_info_loss(q, k, None, 0.05, dtype=torch.float64)
-    assert (dq1.double() - rdq).abs().max().item() <= 3e-2 * rdq.abs().max().item()
-    assert (dk1.double() - rdk).abs().max().item() <= 3e-2 * rdk.abs().max().item()
+    assert (res[2][1].double() - rdq).abs().max().item() <= 3e-2 * rdq.abs().max().item()
+    assert (res[2][2].double() - rdk).abs().max().item() <= 3e-2 * rdk.abs().max().item()
+    _assert_rows_close(res[2][1].numpy(), rdq.numpy(), "bf16")
+    _assert_rows_close(res[2][2].numpy(), rdk.numpy(), "bf16")
 
 
 def test_loss_step_is_cuda_graph_capturable():
