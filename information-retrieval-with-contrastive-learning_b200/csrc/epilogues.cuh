@@ -46,6 +46,7 @@ struct TopKEpilogue {
     int seed_chunks;
   };
   static constexpr bool kUsesScratch = false;
+  static constexpr bool kStagesColumns = false;
   TopKList<KCAP> list;
   uint64_t bnd;
 

@@ -9,6 +9,7 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include "ptx.cuh"
 #include "topk.cuh"
 
 namespace drs {
@@ -44,6 +45,7 @@ struct LseEpilogue {
     const float* col_scale;  // [rows_b] or nullptr
   };
   static constexpr bool kUsesScratch = false;
+  static constexpr bool kStagesColumns = false;
   float m, l;
 
   __device__ __forceinline__ void begin_unit(const Params&, int, int, int) {
@@ -140,8 +142,14 @@ struct GradLogitEpilogue {
                              // not computed (GemmShape::skip_below_diagonal): a chunk above it is also written transposed
   };
   static constexpr bool kUsesScratch = sizeof(OutT) == 2;
+  static constexpr bool kStagesColumns = sizeof(OutT) == 2;   // mode 0 needs the LSE of every COLUMN: staged per tile by the kernel
   uint8_t* scratch = nullptr;  // per-warp smem staging (tensor-core kernel only), see store32_coalesced
+  const float* cols = nullptr; // the 32 column LSEs of the current chunk in shared memory (tensor-core kernel only)
   float li, li2, c;
+
+  __device__ __forceinline__ float column_value(const Params& p, int col) const {
+    return (p.mode == 0 && col < p.rows_b) ? __ldg(p.lse2 + col) : 0.f;
+  }
 
   __device__ __forceinline__ void begin_unit(const Params& p, int row, int, int) {
     const int r = min(row, p.rows_a - 1);
@@ -176,7 +184,9 @@ struct GradLogitEpilogue {
   __device__ __forceinline__ void store32_coalesced(const Params& p, int row, int col0, const float (&h)[32]) const {
     const int lane = threadIdx.x & 31;
     constexpr int kPitch = 80;  // 64 data + 16 pad: conflict-free 16-byte writes, one 2-way conflict on the reads
-    uint8_t* mine = scratch + lane * kPitch;
+    // explicit shared-space accesses: through the generic `scratch` pointer these were LD.E / ST.E (long scoreboard)
+    const uint32_t base = smem_u32(scratch);
+    const uint32_t mine = base + lane * kPitch;
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
       uint4 pk;
@@ -188,14 +198,15 @@ struct GradLogitEpilogue {
       pk.y = *reinterpret_cast<uint32_t*>(&t1);
       pk.z = *reinterpret_cast<uint32_t*>(&t2);
       pk.w = *reinterpret_cast<uint32_t*>(&t3);
-      *reinterpret_cast<uint4*>(mine + 2 * j) = pk;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(mine + 2 * j), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
     }
     __syncwarp();
     const int row0 = row - lane, piece = lane & 3;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = (lane >> 2) + 8 * i;
-      const uint4 val = *reinterpret_cast<const uint4*>(scratch + r * kPitch + 16 * piece);
+      uint4 val;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(base + r * kPitch + 16 * piece) : "memory");
       if (row0 + r < p.rows_a)
         *reinterpret_cast<uint4*>(p.out + static_cast<long long>(row0 + r) * p.ld_out + col0 + 8 * piece) = val;
     }
@@ -248,10 +259,12 @@ struct GradLogitEpilogue {
         if (!live && !staged) return;  // (a dead lane still takes part in the staged store of its warp)
         float h[32];
         if (p.mode == 0) {
-          const float4* lp = reinterpret_cast<const float4*>(p.lse2 + col0);  // col0 % 32 == 0: 16-byte aligned
+          // column LSEs: from the kernel's per-tile shared-memory stage when there is one (broadcast reads, no
+          // global-memory latency inside the chunk), else from global memory
+          const float4* lp = reinterpret_cast<const float4*>(cols != nullptr ? cols : p.lse2 + col0);  // 16-byte aligned
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 lj = __ldg(lp + j4);
+            const float4 lj = cols != nullptr ? lp[j4] : __ldg(lp + j4);
             const float ljs[4] = {lj.x, lj.y, lj.z, lj.w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -364,6 +377,7 @@ struct StoreEpilogue {
     int accumulate;  // 1: out += value
   };
   static constexpr bool kUsesScratch = false;
+  static constexpr bool kStagesColumns = false;
   __device__ __forceinline__ void begin_unit(const Params&, int, int, int) {}
   __device__ __forceinline__ void chunk(const Params& p, int row, int col0, const uint32_t (&v)[32]) {
     if (row >= p.rows_a) return;
@@ -435,6 +449,54 @@ pack_transpose_kernel(const float* __restrict__ s0, const float* __restrict__ s1
   }
 }
 
+// The InfoNCE operands: F = cat(q, k) [R = 2N][C] fp32 -> bf16 F (row-major) and bf16 F^T [C][R], 64 x 64 tiles, every
+// global access a full 128-byte line (float4 loads, 8-byte / 16-byte bf16 stores).  C % 4 == 0, R % 8 == 0 (the bf16
+// path requires dim % 8 and n % 4).  Also zeroes the word the fused loss reduction counts finished blocks in.
+__global__ void __launch_bounds__(256)
+pack_cat_bf16_kernel(const float* __restrict__ s0, const float* __restrict__ s1, int split, int R, int C,
+                     __nv_bfloat16* __restrict__ obf, __nv_bfloat16* __restrict__ obf_t, unsigned int* __restrict__ zero_word) {
+  __shared__ float tile[64][65];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && zero_word != nullptr) *zero_word = 0u;
+  const int tiles_c = (C + 63) / 64, tiles_r = (R + 63) / 64;
+  const int tid = threadIdx.x;
+  for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const int r0 = (t / tiles_c) * 64, c0 = (t % tiles_c) * 64;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + (tid >> 4) + 16 * i, c = c0 + (tid & 15) * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < R && c < C) {
+        x = *reinterpret_cast<const float4*>(r < split ? s0 + static_cast<size_t>(r) * C + c : s1 + static_cast<size_t>(r - split) * C + c);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(obf + static_cast<size_t>(r) * C + c) = pk;
+      }
+      float* dst = &tile[(tid >> 4) + 16 * i][(tid & 15) * 4];
+      dst[0] = x.x; dst[1] = x.y; dst[2] = x.z; dst[3] = x.w;
+    }
+    __syncthreads();
+    if (obf_t != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int cl = (tid >> 3) + 32 * i, rl = (tid & 7) * 8;   // output row = column of the tile, 8 consecutive r per thread
+        const int c = c0 + cl, r = r0 + rl;
+        if (c < C && r < R) {
+          uint32_t w[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            __nv_bfloat162 v = __floats2bfloat162_rn(tile[rl + 2 * h][cl], tile[rl + 2 * h + 1][cl]);
+            w[h] = *reinterpret_cast<uint32_t*>(&v);
+          }
+          *reinterpret_cast<uint4*>(obf_t + static_cast<size_t>(c) * R + r) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // (m, l) pairs in the log2 domain: l_a 2^m_a + l_b 2^m_b
 __device__ __forceinline__ void lse_combine(float& m, float& l, float m2, float l2) {
   const float mn = fmaxf(m, m2);
@@ -448,39 +510,74 @@ __device__ __forceinline__ void lse_combine(float& m, float& l, float m2, float 
 //   part   [rows][slots]          in-batch / prototype partials
 //   part_q [rows_q][slots_q]      optional queue partials of row (i mod rows_q)  (the .repeat(2,1), :80)
 //   include_pos: the positive logit pos[i] is an extra column (MoCo form, :30-36)
+//   loss (optional): loss[0] = loss_scale * sum_i (lse_i - pos_i), fused in: every block leaves the sum of its 8 rows in
+//   `partials`, the block that finishes last adds them up in index order (deterministic) and resets `counter` (which
+//   the caller zeroed once, before the first call on this workspace -- the pack kernel does)
 __global__ void __launch_bounds__(256)
 lse_rows_kernel(const float2* __restrict__ part, int slots, const float2* __restrict__ part_q, int slots_q, int rows_q,
                 const float* __restrict__ pos, int include_pos, int rows, float* __restrict__ lse,
-                float* __restrict__ lse2) {
+                float* __restrict__ lse2, float loss_scale = 0.f, float* __restrict__ loss = nullptr,
+                float* __restrict__ partials = nullptr, unsigned int* __restrict__ counter = nullptr) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  float m = -INFINITY, l = 0.f;
-  if (include_pos && lane == 0) {
-    m = pos[row] * kLog2e;
-    l = 1.f;
-  }
-  for (int s = lane; s < slots; s += 32) {
-    const float2 p = part[static_cast<size_t>(row) * slots + s];
-    lse_combine(m, l, p.x, p.y);
-  }
-  if (part_q != nullptr) {
-    const int r = row % rows_q;
-    for (int s = lane; s < slots_q; s += 32) {
-      const float2 p = part_q[static_cast<size_t>(r) * slots_q + s];
+  float term = 0.f;
+  if (row < rows) {
+    float m = -INFINITY, l = 0.f;
+    if (include_pos && lane == 0) {
+      m = pos[row] * kLog2e;
+      l = 1.f;
+    }
+    for (int s = lane; s < slots; s += 32) {
+      const float2 p = part[static_cast<size_t>(row) * slots + s];
       lse_combine(m, l, p.x, p.y);
     }
-  }
+    if (part_q != nullptr) {
+      const int r = row % rows_q;
+      for (int s = lane; s < slots_q; s += 32) {
+        const float2 p = part_q[static_cast<size_t>(r) * slots_q + s];
+        lse_combine(m, l, p.x, p.y);
+      }
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
-    const float l2 = __shfl_xor_sync(0xffffffffu, l, o);
-    lse_combine(m, l, m2, l2);
-  }
-  if (lane == 0) {
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+      const float l2 = __shfl_xor_sync(0xffffffffu, l, o);
+      lse_combine(m, l, m2, l2);
+    }
     const float v = m + log2f(l);
-    lse2[row] = v;
-    lse[row] = v * kLn2;
+    if (lane == 0) {
+      lse2[row] = v;
+      lse[row] = v * kLn2;
+    }
+    if (loss != nullptr) term = v * kLn2 - pos[row];
+  }
+  if (loss == nullptr) return;
+  __shared__ float warp_term[8];
+  __shared__ bool last;
+  if (lane == 0) warp_term[threadIdx.x >> 5] = term;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+    for (int w = 0; w < 8; ++w) sum += warp_term[w];
+    partials[blockIdx.x] = sum;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  __shared__ float red[256];
+  float acc = 0.f;                                     // fixed assignment of partials to threads, fixed tree
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += 256) acc += __ldcg(partials + i);
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    loss[0] = loss_scale * red[0];
+    *counter = 0u;
   }
 }
 
