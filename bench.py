@@ -77,7 +77,7 @@ class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
 
     def __init__(self, index):
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.index, self.samples, self.power, self.reasons, self.max_mhz = index, [], [], set(), None
         self._stop = threading.Event()
         self._thread = None
         try:
@@ -95,12 +95,15 @@ class ClockSampler:
                 mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
                 mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 self.samples.append(mhz)
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
                 for bit, name in _REASONS.items():
                     if mask & bit:
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.05)
+            time.sleep(self.period)
+
+    period = 0.05
 
     def __enter__(self):
         if self.nv is not None:
@@ -116,7 +119,8 @@ class ClockSampler:
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
-        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "power_w": statistics.median(self.power) if self.power else None}
 
 
 # --------------------------------------------------------------------------------- CPU reference arm
@@ -204,12 +208,20 @@ def bench_other_configs(torch, drs_b200, dev, peaks, shard, queries, rank, world
     # configs[0]: 1k claims x 100k x 768 fp32, top-5 (the reference's CPU-runnable case)
     c32 = shard[:100_000].float()
     q32 = queries[:1000].float()
-    ms = timed(lambda: drs_b200.search(q32, c32, 5), 5)
+    ms = timed(lambda: drs_b200.search(q32, c32, 5), 10)
     tf32 = 2.0 * 1000 * 100_000 * dim / (ms * 1e-3) / 1e12
+    drs_b200.set_option("search.fp32_mode", 1)
+    try:
+        ms_ffma = timed(lambda: drs_b200.search(q32, c32, 5), 5)
+    finally:
+        drs_b200.set_option("search.fp32_mode", 0)
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     ffma_roof = sms * 64 * 2 * 1.965e9 / 1e12      # a 3-register FFMA issues every 2 cycles per SM sub-partition: 64 FMA/clk/SM
-    rec = {"workload": "1000 claims x 100000 x 768 fp32, top-5 (exact FFMA path)", "ms_per_step": ms,
-           "claims_per_s": 1000 / (ms * 1e-3), "tflops_fp32": tf32, "ffma_roof_tflops": ffma_roof, "ffma_frac": tf32 / ffma_roof}
+    rec = {"workload": "1000 claims x 100000 x 768 fp32, top-5 (fp32 operands on tcgen05: 3 x TF32 split, fp32 accumulate; 1e-5 parity bar)",
+           "ms_per_step": ms, "claims_per_s": 1000 / (ms * 1e-3), "tflops_fp32_effective": tf32,
+           "tensor_frac_3xtf32": 3 * tf32 / (peaks["tflops"] / 2),
+           "ffma_checker_path": {"ms_per_step": ms_ffma, "tflops_fp32": 2.0 * 1000 * 100_000 * dim / (ms_ffma * 1e-3) / 1e12,
+                                 "ffma_roof_tflops": ffma_roof}}
     if rank == 0:
         from oracle import dense_topk
         qc, cc = q32.cpu(), c32.cpu()
@@ -302,7 +314,10 @@ def bench_infonce(torch, drs_b200, dev, peaks, n=4096, dim=768, temperature=0.05
             "tflops": flops / (ms * 1e-3) / 1e12,
             "mma_frac": flops / (ms * 1e-3) / 1e12 / peaks["tflops"],
             "forward_logit_bytes_not_materialised": 4 * (2 * n) ** 2,
-            "backward_workspace_bytes": _infonce_workspace_bytes(n, dim)}
+            "backward_grad_logit_bytes_written": ((2 * n // 256) * (2 * n // 256 + 1) // 2) * 256 * 256 * 2,
+            "backward_grad_logit_note": "H = dL/dlogits is symmetric: only its 256 x 256 tiles on and above the diagonal are computed and "
+                                        "stored (bf16, once); the dF = H F GEMM reads the others transposed (MN-major tcgen05 operand)",
+            "workspace_bytes": _infonce_workspace_bytes(n, dim)}
 
 
 def _infonce_workspace_bytes(n, dim):
@@ -460,8 +475,11 @@ def run_b200(args):
             rprof = []
             for _ in range(3):
                 index.search(qs, k)
-            reps = 10 if bq <= 256 else 5
-            ms = timed_loop(lambda: index.search(qs, k, profile=rprof), reps) / reps
+            reps = 20 if bq <= 256 else 10
+            sampler = ClockSampler(local_rank)
+            sampler.period = 0.005
+            with sampler:
+                ms = timed_loop(lambda: index.search(qs, k, profile=rprof), reps) / reps
             kms = sum(a.elapsed_time(b) for a, b in rprof) / max(1, len(rprof))
             if world > 1:
                 t = torch.tensor([kms], device=dev)
@@ -473,11 +491,18 @@ def run_b200(args):
             gbs = byt / (kms * 1e-3) / 1e9
             tfl = flp / (kms * 1e-3) / 1e12
             t_hbm, t_mma = byt / (peaks["hbm_gbs"] * 1e9), flp / (peaks["tflops"] * 1e12)
-            regimes.append({"claims_per_pass": bq, "ms_per_step": ms, "scan_kernel_ms": kms,
-                            "claims_per_s": bq / (ms * 1e-3), "hbm_gbs_per_gpu": gbs,
-                            "hbm_frac": gbs / peaks["hbm_gbs"], "mma_frac": tfl / peaks["tflops"],
-                            "bound": "hbm" if t_hbm >= t_mma else "tensor",
-                            "roofline_frac": max(t_hbm, t_mma) / (kms * 1e-3)})
+            clk = sampler.summary()
+            row = {"claims_per_pass": bq, "ms_per_step": ms, "scan_kernel_ms": kms,
+                   "claims_per_s": bq / (ms * 1e-3), "hbm_gbs_per_gpu": gbs,
+                   "hbm_frac": gbs / peaks["hbm_gbs"], "mma_frac": tfl / peaks["tflops"],
+                   "bound": "hbm" if t_hbm >= t_mma else "tensor",
+                   "roofline_frac": max(t_hbm, t_mma) / (kms * 1e-3),
+                   "sm_mhz": clk["sm_mhz"], "power_w": clk.get("power_w")}
+            if clk["sm_mhz"]:
+                # the tensor pipes' own peak at the clock the row actually ran at: SMs x 8192 dense bf16 flop / clock
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                row["tensor_frac_at_clock"] = tfl * 1e12 / (sms * 8192.0 * clk["sm_mhz"] * 1e6)
+            regimes.append(row)
 
     # ---- device-resident throughput (`value`) with the scan kernel bracketed by events (roofline)
     prof = []
@@ -515,6 +540,25 @@ def run_b200(args):
                                  else "NCCL all-gather + merge_pairs_kernel"),
                         "ms_per_step": exc, "share_of_step": exc / ms_per_step, "local_scan_select_ms": loc,
                         "nvlink_bytes_out_per_rank": (world - 1) * per * k * 12 * 2 if index.exchange == "p2p" else None}
+    if exchange_rec is not None:
+        # the in-step figure includes waiting for the slowest rank's scan (clock skew between GPUs under the power
+        # cap); the exchange on its own, all ranks released together by a barrier, is measured here outside the loop
+        sync_ms = []
+        lists = index.local_lists(queries, k)
+        for _ in range(5):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            index.exchange_lists(*lists)
+            e1.record()
+            torch.cuda.synchronize()
+            sync_ms.append(e0.elapsed_time(e1))
+        t = torch.tensor([min(sync_ms)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        exchange_rec["ms_in_step_incl_rank_skew"] = exchange_rec.pop("ms_per_step")
+        exchange_rec["share_of_step_incl_rank_skew"] = exchange_rec.pop("share_of_step")
+        exchange_rec["kernel_ms"] = t.item()
+        exchange_rec["kernel_share_of_step"] = t.item() / ms_per_step
     value = nq / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API with HOST buffers: H2D of the claims, D2H of the result
@@ -595,7 +639,10 @@ def run_b200(args):
         if regimes:
             line["small_batch_regime"] = regimes
             line["small_batch_regime_note"] = (f"hbm_frac = algorithmic bytes / scan time / {peaks['hbm_gbs']:.0f} GB/s, the measured "
-                                               "copy bandwidth (read + write); a read-only stream can exceed it, so hbm_frac > 1 is possible")
+                                               "copy bandwidth (read + write); a read-only stream can exceed it, so hbm_frac > 1 is possible.  "
+                                               "Near the ridge (256..1024 claims per pass) HBM and the tensor pipes are both busy and the 1 kW power cap "
+                                               "pulls the SM clock far below the 1335 MHz the sustained cuBLAS peak was measured at (sm_mhz, power_w per row; "
+                                               "profiles/r02_ridge_b256_kernel_metrics.json); tensor_frac_at_clock = achieved flops / (SMs x 8192 x that clock)")
         if infonce_line:
             line["infonce_config"] = infonce_line
         if other_configs:

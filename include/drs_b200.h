@@ -144,6 +144,18 @@ int drs_exchange_sliced(const float* local_scores, const int64_t* local_ids, int
                         float* out_scores, int64_t* out_ids, void* stream);
 
 /*
+ * Peer-mapped device buffers for the two exchange kernels above, over CUDA IPC: every rank (one process per GPU of
+ * one box) allocates its buffer with drs_peer_alloc -- zero-filled, which is the state both kernels' flags and epochs
+ * start from -- hands the 64-byte handle to its peers (any transport: the Python side all-gathers them through
+ * torch.distributed), and maps each peer's buffer with drs_peer_open (peer access is enabled on first use).
+ * Close every mapping and free the buffer only after all ranks have finished their last exchange call.
+ */
+int drs_peer_alloc(size_t bytes, void** ptr, unsigned char handle[64]);
+int drs_peer_open(const unsigned char handle[64], void** ptr);
+int drs_peer_close(void* ptr);
+int drs_peer_free(void* ptr);
+
+/*
  * Candidate-restricted re-rank: score each claim against ITS OWN candidate rows only and keep the best k.
  * Replaces: the dense stage of the report's pipeline "TF-IDF top-100 -> contrastive re-rank -> top-15"
  * (report.pdf section 3.2) at the call site src/evaluation.py:105-116, fed by the sparse candidates of

@@ -42,6 +42,10 @@ _SIGNATURES = {
                                        c_sz, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "drs_exchange_sliced_bytes": (c_int, [c_i64, c_i64, c_int, ctypes.POINTER(c_sz)]),
     "drs_exchange_sliced": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "drs_peer_alloc": (c_int, [c_sz, ctypes.POINTER(c_vp), ctypes.POINTER(ctypes.c_ubyte * 64)]),
+    "drs_peer_open": (c_int, [ctypes.POINTER(ctypes.c_ubyte * 64), ctypes.POINTER(c_vp)]),
+    "drs_peer_close": (c_int, [c_vp]),
+    "drs_peer_free": (c_int, [c_vp]),
     "drs_merge_shards": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp]),
     "drs_infonce_workspace_bytes": (c_int, [c_i64, c_int, c_i64, c_int, ctypes.POINTER(c_sz)]),
     "drs_infonce_forward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_f32, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),

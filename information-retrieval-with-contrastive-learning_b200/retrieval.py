@@ -409,8 +409,63 @@ class DenseDocRanker(DenseIndex):
         return super().batch_closest_docs(queries, k, num_workers)
 
 
+class _PeerBuffer:
+    """One zero-filled device buffer per rank, mapped into every other rank of the group over CUDA IPC
+    (csrc/exchange_api.inc::drs_peer_*): ``ptrs[r]`` is rank r's buffer as seen from this process."""
+
+    def __init__(self, group, device, world, rank, nbytes):
+        import torch.distributed as dist
+        lib = _lib.load()
+        self.device, self.rank, self.world, self.group = device, rank, world, group
+        self.ptrs, self._own, self._opened = [], None, []
+        with torch.cuda.device(device):
+            ptr, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+            _lib.check(lib.drs_peer_alloc(nbytes, ctypes.byref(ptr), ctypes.byref(handle)))
+            self._own = ptr.value
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+            everyone = torch.empty(world * 64, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(everyone, mine, group=group)
+            handles = everyone.cpu().view(world, 64)
+            err = None
+            for r in range(world):
+                if r == rank:
+                    self.ptrs.append(self._own)
+                    continue
+                h = (ctypes.c_ubyte * 64)(*handles[r].tolist())
+                p = ctypes.c_void_p()
+                try:
+                    _lib.check(lib.drs_peer_open(ctypes.byref(h), ctypes.byref(p)))
+                except RuntimeError as e:             # keep the collectives below balanced, fail afterwards
+                    err = err or e
+                    self.ptrs.append(0)
+                    continue
+                self._opened.append(p.value)
+                self.ptrs.append(p.value)
+            # doubles as the barrier: every rank's buffer is zeroed and mapped before anyone publishes
+            ok = torch.tensor([0 if err else 1], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if not int(ok.item()):
+                self.close()
+                raise RuntimeError(f"peer buffers could not be mapped on every rank ({err or 'a peer failed'})")
+
+    def close(self):
+        """Collective: call on every rank, after the last exchange that used this buffer."""
+        import torch.distributed as dist
+        if self._own is None:
+            return
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)            # no peer is still reading or writing
+            for p in self._opened:
+                lib.drs_peer_close(p)
+            dist.barrier(group=self.group)            # every mapping is closed before the owner frees
+            lib.drs_peer_free(self._own)
+        self._own, self._opened, self.ptrs = None, [], []
+
+
 class _PeerExchange:
-    """Symmetric (peer-mapped) gather buffers and flags for the fused select + exchange + merge kernel
+    """Peer-mapped gather buffers and flags for the fused select + exchange + merge kernel
     (csrc/exchange.cuh): every rank allocates the same layout and maps every peer's copy over NVLink.
 
         [ flags: claim blocks x world u32 | parity 0: scores, ids | parity 1: scores, ids ]
@@ -419,8 +474,6 @@ class _PeerExchange:
     MAX_NQ = 1 << 17
 
     def __init__(self, group, device, world, rank, capacity):
-        import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm
         self.world, self.rank, self.capacity = world, rank, int(capacity)         # capacity: nq * k entries
         need = ctypes.c_size_t(0)
         _lib.check(_lib.load().drs_exchange_flag_bytes(self.MAX_NQ, world, ctypes.byref(need)))
@@ -428,12 +481,8 @@ class _PeerExchange:
         self.s_bytes = (world * self.capacity * 4 + 255) // 256 * 256
         self.i_bytes = (world * self.capacity * 8 + 255) // 256 * 256
         total = self.flag_bytes + 2 * (self.s_bytes + self.i_bytes)
-        self.buf = symm.empty(total, dtype=torch.uint8, device=device)
-        self.buf.zero_()
-        torch.cuda.synchronize(device)
-        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
-        self.handle.barrier()                         # every rank's flags are zero before anyone publishes
-        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.buf = _PeerBuffer(group, device, world, rank, total)
+        self.ptrs = self.buf.ptrs
         self.calls = torch.zeros(1, dtype=torch.int32, device=device)      # this rank's completed exchange calls
         arr = ctypes.c_void_p * world
         base = self.flag_bytes                                             # parity-0 buffers; parity 1 = + parity_stride
@@ -442,9 +491,12 @@ class _PeerExchange:
         self.id_ptrs = arr(*[p + base + self.s_bytes for p in self.ptrs])
         self.flag_ptrs = arr(*self.ptrs)
 
+    def close(self):
+        self.buf.close()
+
 
 class _SlicedExchange:
-    """Symmetric buffer for the query-sliced exchange (csrc/exchange.cuh::exchange_sliced_kernel): per rank
+    """Peer-mapped buffer for the query-sliced exchange (csrc/exchange.cuh::exchange_sliced_kernel): per rank
 
         [ flags1 | flags2 | parity 0: gather scores, gather ids, result scores, result ids | parity 1: ... ]
 
@@ -453,18 +505,15 @@ class _SlicedExchange:
     MAX_NQ = 1 << 18
 
     def __init__(self, group, device, world, rank, max_entries):
-        import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm
         self.world, self.rank, self.max_entries = world, rank, int(max_entries)
         need = ctypes.c_size_t(0)
         _lib.check(_lib.load().drs_exchange_sliced_bytes(self.MAX_NQ, self.max_entries, world, ctypes.byref(need)))
-        self.buf = symm.empty(need.value, dtype=torch.uint8, device=device)
-        self.buf.zero_()
-        torch.cuda.synchronize(device)
-        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
-        self.handle.barrier()                         # every rank's flags are zero before anyone publishes
-        self.bases = (ctypes.c_void_p * world)(*[int(p) for p in self.handle.buffer_ptrs])
+        self.buf = _PeerBuffer(group, device, world, rank, need.value)
+        self.bases = (ctypes.c_void_p * world)(*self.buf.ptrs)
         self.calls = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def close(self):
+        self.buf.close()
 
 
 class ShardedDenseIndex:
@@ -474,8 +523,9 @@ class ShardedDenseIndex:
     The per-rank (score, global id) lists are then exchanged and merged by (score desc, id asc), which
     makes the result identical to a single-GPU search of the whole corpus.  Two exchanges:
 
-    * ``exchange='p2p'`` (NVLink peer memory, csrc/exchange.cuh; needs the NCCL backend's symmetric memory, <= 8
-      ranks, no empty shard).  k <= 16: ONE kernel per search selects the shard's top-k, stores it into every peer's
+    * ``exchange='p2p'`` (NVLink peer memory, csrc/exchange.cuh; buffers mapped across the ranks with CUDA IPC, so
+      one process per GPU of ONE box; needs a CUDA-capable backend (nccl) for the handle exchange, <= 8 ranks, no
+      empty shard).  k <= 16: ONE kernel per search selects the shard's top-k, stores it into every peer's
       buffer, waits on per-claim-block flags and merges.  Larger k (BASELINE configs[4]: top-100): the QUERY-SLICED
       kernel -- rank s receives only the lists of its slice of the claims, merges them and stores the final lists
       into every rank's result buffer (world x fewer bytes and merges per GPU than gathering everything everywhere);
@@ -526,6 +576,8 @@ class ShardedDenseIndex:
                     raise RuntimeError(f"exchange='p2p': peer memory could not be mapped on every rank ({err})")
                 self.exchange, self._peer = "nccl", None
                 return None
+            if self._peer is not None:
+                self._peer.close()                    # collective: every rank regrows at the same call
             self._peer = peer
         return self._peer
 
@@ -545,8 +597,17 @@ class ShardedDenseIndex:
                     raise RuntimeError(f"exchange='p2p': peer memory could not be mapped on every rank ({err})")
                 self.exchange, self._sliced = "nccl", None
                 return None
+            if self._sliced is not None:
+                self._sliced.close()
             self._sliced = sl
         return self._sliced
+
+    def close(self):
+        """Release the peer-mapped exchange buffers (collective; optional -- process exit releases them too)."""
+        for ex in (self._peer, self._sliced):
+            if ex is not None:
+                ex.close()
+        self._peer = self._sliced = None
 
     def search(self, queries: torch.Tensor, k: int = 1, profile: Optional[list] = None, timing: Optional[dict] = None):
         """``timing``: optional dict; CUDA event pairs are stored under 'local' (scan + select of this shard) and
@@ -566,21 +627,38 @@ class ShardedDenseIndex:
             return ev
 
         t0 = mark()
+        slot_s, slot_i = self.local_lists(queries, kk, profile)
+        t1 = mark()
+        out = self.exchange_lists(slot_s, slot_i)
+        t2 = mark()
+        if timing is not None:
+            timing.setdefault("local", []).append((t0, t1))
+            timing.setdefault("exchange", []).append((t1, t2))
+        return out
+
+    def local_lists(self, queries: torch.Tensor, kk: int, profile: Optional[list] = None):
+        """This shard's sorted (score, GLOBAL id) lists, [nq, kk] each, padded with (-inf, -1) when the shard holds
+        fewer than kk rows -- fixed-size slots, so every rank contributes the same number of bytes."""
+        nq = queries.shape[0]
+        dev = self.local.device
         s, i = (self.local.search(queries, min(kk, max(self.local.num_docs, 1)), profile=profile)
                 if self.local.num_docs else (None, None))
-        # fixed-size slots so every rank contributes the same number of bytes
         if s is not None and s.shape[1] == kk:
-            slot_s, slot_i = s, i
-        else:
-            slot_s = torch.full((nq, kk), float("-inf"), dtype=torch.float32, device=dev)
-            slot_i = torch.full((nq, kk), -1, dtype=torch.int64, device=dev)
-            if s is not None:
-                slot_s[:, : s.shape[1]] = s
-                slot_i[:, : i.shape[1]] = i
-        t1 = mark()
+            return s, i
+        slot_s = torch.full((nq, kk), float("-inf"), dtype=torch.float32, device=dev)
+        slot_i = torch.full((nq, kk), -1, dtype=torch.int64, device=dev)
+        if s is not None:
+            slot_s[:, : s.shape[1]] = s
+            slot_i[:, : i.shape[1]] = i
+        return slot_s, slot_i
+
+    def exchange_lists(self, slot_s: torch.Tensor, slot_i: torch.Tensor):
+        """The one exchange step on per-shard lists (a collective): query-sliced peer-memory kernel, or NCCL
+        all-gather + merge kernel.  Returns the merged [nq, kk] (scores, ids), identical on every rank."""
+        nq, kk = slot_s.shape
+        dev = self.local.device
         if self.world == 1:
             return slot_s, slot_i
-        out = None
         per = -(-nq // self.world)
         if self.exchange == "p2p" and 0 < nq <= _SlicedExchange.MAX_NQ and kk <= _lib.DRS_MAX_K:
             sl = self._sliced_exchange(per * self.world * kk)
@@ -592,15 +670,9 @@ class ShardedDenseIndex:
                                                                sl.bases, sl.MAX_NQ, sl.max_entries, sl.calls.data_ptr(),
                                                                out_s.data_ptr(), out_i.data_ptr(),
                                                                torch.cuda.current_stream(dev).cuda_stream))
-                out = (out_s, out_i)
-        if out is None:
-            all_s, all_i = all_gather_topk(slot_s, slot_i, self.group)
-            out = merge_shards(all_s, all_i)
-        t2 = mark()
-        if timing is not None:
-            timing.setdefault("local", []).append((t0, t1))
-            timing.setdefault("exchange", []).append((t1, t2))
-        return out
+                return out_s, out_i
+        all_s, all_i = all_gather_topk(slot_s.contiguous(), slot_i.contiguous(), self.group)
+        return merge_shards(all_s, all_i)
 
     def _search_p2p(self, queries: torch.Tensor, kk: int, profile: Optional[list]):
         loc = self.local

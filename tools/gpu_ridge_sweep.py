@@ -1,6 +1,9 @@
 #!/usr/bin/env python
-"""Perf probe (test tooling): the ridge between the two roofs -- claims per pass x CTA group x L2 prefetch distance.
-    python tools/gpu_ridge_sweep.py [corpus rows] [csv of claim counts] [csv of prefetch distances]"""
+"""Perf probe (test tooling): the ridge between the two roofs -- claims per pass x CTA group.
+    python tools/gpu_ridge_sweep.py [corpus rows] [csv of claim counts]
+(An L2 prefetch of the next corpus tile by the producer -- cp.async.bulk.prefetch.tensor -- was tried here: it made
+every point SLOWER, 2.66 -> 4.86 ms at 128 claims x 12M rows: the TMA unit, not HBM latency, is what the extra
+requests queue behind.)"""
 import os
 import sys
 
@@ -25,7 +28,6 @@ def main():
     dev = torch.device("cuda:0")
     nc = int(sys.argv[1]) if len(sys.argv) > 1 else 8_000_000
     nqs = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "128,256,384,512,1024,2048").split(",")]
-    pfs = [int(x) for x in (sys.argv[3] if len(sys.argv) > 3 else "0,1,2").split(",")]
     g = torch.Generator(device=dev).manual_seed(1)
     c = torch.empty(nc, 768, dtype=torch.bfloat16, device=dev)
     for r0 in range(0, nc, 1 << 20):
@@ -43,16 +45,13 @@ def main():
             if cg == 1 and nq > 1024:
                 continue
             drs.set_option("search.cta_group", cg)
-            for pf in pfs:
-                drs.set_option("tune.l2_prefetch", pf)
-                ms = scan_ms(q, c, 10)
-                s, i = drs.search(q, c, 10)
-                if nq not in ref:
-                    ref[nq] = (s.clone(), i.clone())
-                same = torch.equal(i, ref[nq][1]) and torch.equal(s, ref[nq][0])
-                line += f" cg{cg}/pf{pf}: {ms:6.3f} ({roof / ms * 100:5.1f} %){'' if same else ' DIFF'}"
+            ms = scan_ms(q, c, 10)
+            s, i = drs.search(q, c, 10)
+            if nq not in ref:
+                ref[nq] = (s.clone(), i.clone())
+            same = torch.equal(i, ref[nq][1]) and torch.equal(s, ref[nq][0])
+            line += f" cg{cg}: {ms:6.3f} ({roof / ms * 100:5.1f} %){'' if same else ' DIFF'}"
         drs.set_option("search.cta_group", 0)
-        drs.set_option("tune.l2_prefetch", -1)
         print(line, flush=True)
 
 
