@@ -207,8 +207,11 @@ struct GradLogitEpilogue {
       const int r = (lane >> 2) + 8 * i;
       uint4 val;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(base + r * kPitch + 16 * piece) : "memory");
+      // evict-last: the next kernel (dF = H F) reads this matrix back; it should still be in L2 then
       if (row0 + r < p.rows_a)
-        *reinterpret_cast<uint4*>(p.out + static_cast<long long>(row0 + r) * p.ld_out + col0 + 8 * piece) = val;
+        asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p.out + static_cast<long long>(row0 + r) * p.ld_out + col0 + 8 * piece),
+                     "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w), "l"(kEvictLast)
+                     : "memory");
     }
     __syncwarp();  // the staging area is reused by the next chunk (store32_mirrored, if any, only reads it)
   }

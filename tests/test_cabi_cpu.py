@@ -64,6 +64,27 @@ def test_null_and_range_checks_return_codes(lib):
     assert lib.drs_infonce_forward(None, None, None, 4, 64, 0, 20.0, 0, None, None, None, 0, None) == 1
 
 
+def test_exchange_layout_and_peer_entry_points_validate_without_a_gpu(lib):
+    """The query-sliced exchange lays its per-rank buffer out on the host (pure arithmetic): flags, then two parities
+    of {gather scores, gather ids, result scores, result ids}; arguments are validated before any CUDA call."""
+    need = ctypes.c_size_t(0)
+    assert lib.drs_exchange_sliced_bytes(65536, 65536 * 100 + 800, 8, ctypes.byref(need)) == 0
+    entries = 65536 * 100 + 800
+    assert need.value >= 2 * 24 * entries and need.value % 256 == 0          # 2 parities x (4 + 8 + 4 + 8) bytes per entry
+    small = ctypes.c_size_t(0)
+    assert lib.drs_exchange_sliced_bytes(1000, 10000, 2, ctypes.byref(small)) == 0 and small.value < need.value
+    assert lib.drs_exchange_sliced_bytes(0, 10, 2, ctypes.byref(need)) == 1
+    assert lib.drs_exchange_sliced_bytes(10, 10, 9, ctypes.byref(need)) == 1   # at most 8 peers
+    assert lib.drs_exchange_sliced_bytes(10, 10, 2, None) == 1
+    assert lib.drs_exchange_sliced(None, None, 4, 5, 0, 2, None, 4, 100, None, None, None, None) == 1
+    assert lib.drs_peer_alloc(0, None, None) == 1 and lib.drs_peer_open(None, None) == 1
+    assert lib.drs_peer_close(None) == 0 and lib.drs_peer_free(None) == 0      # nothing to release
+    _lib.set_option("tune.cooperative", 0)
+    assert _lib.get_option("tune.cooperative") == 0
+    _lib.set_option("tune.cooperative", 1)
+    assert _lib.get_option("search.fp32_mode") == 0 and _lib.get_option("tune.symmetric_grad") == 2
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib._build, "LIB", str(tmp_path / "libdrs_b200.so"))
