@@ -497,11 +497,7 @@ def run_b200(args):
                    "hbm_frac": gbs / peaks["hbm_gbs"], "mma_frac": tfl / peaks["tflops"],
                    "bound": "hbm" if t_hbm >= t_mma else "tensor",
                    "roofline_frac": max(t_hbm, t_mma) / (kms * 1e-3),
-                   "sm_mhz": clk["sm_mhz"], "power_w": clk.get("power_w")}
-            if clk["sm_mhz"]:
-                # the tensor pipes' own peak at the clock the row actually ran at: SMs x 8192 dense bf16 flop / clock
-                sms = torch.cuda.get_device_properties(dev).multi_processor_count
-                row["tensor_frac_at_clock"] = tfl * 1e12 / (sms * 8192.0 * clk["sm_mhz"] * 1e6)
+                   "sm_mhz": clk["sm_mhz"], "power_w": clk.get("power_w"), "clock_reasons": clk["reasons"]}
             regimes.append(row)
 
     # ---- device-resident throughput (`value`) with the scan kernel bracketed by events (roofline)
@@ -641,8 +637,8 @@ def run_b200(args):
             line["small_batch_regime_note"] = (f"hbm_frac = algorithmic bytes / scan time / {peaks['hbm_gbs']:.0f} GB/s, the measured "
                                                "copy bandwidth (read + write); a read-only stream can exceed it, so hbm_frac > 1 is possible.  "
                                                "Near the ridge (256..1024 claims per pass) HBM and the tensor pipes are both busy and the 1 kW power cap "
-                                               "pulls the SM clock far below the 1335 MHz the sustained cuBLAS peak was measured at (sm_mhz, power_w per row; "
-                                               "profiles/r02_ridge_b256_kernel_metrics.json); tensor_frac_at_clock = achieved flops / (SMs x 8192 x that clock)")
+                                               "pulls the SM clock far below the 1335 MHz the sustained cuBLAS peak was measured at (median NVML sm_mhz and power_w "
+                                               "per row -- instantaneous readings, noisy; profiles/r02_ridge_b256_kernel_metrics.json has ncu's clock for one such launch)")
         if infonce_line:
             line["infonce_config"] = infonce_line
         if other_configs:
