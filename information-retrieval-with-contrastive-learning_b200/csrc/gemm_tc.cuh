@@ -122,7 +122,7 @@ struct GemmCfg {
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;  // 16-bit, 256-wide: 4 (CG 1) / 6 (CG 2); fp32 split: 2 / 3
   static constexpr int BAR_BYTES = 256;
   static constexpr int EPI_SCRATCH_PER_WARP = 2560;  // 32 rows x (64 + 16 pad) bytes: staging for coalesced epilogue stores
-  static constexpr int COL_STAGE_BYTES = 2 * 256 * 4;   // two tiles' worth of per-column values (Epi::kStagesColumns)
+  static constexpr int COL_STAGE_BYTES = 8 * 128 * 4;   // per epilogue warp: the values of its 128 columns of a tile (Epi::kStagesColumns)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 8 * EPI_SCRATCH_PER_WARP + COL_STAGE_BYTES + 1024;  // + alignment slack
   static constexpr int EPI_GROUPS = 2;     // epilogue warps per TMEM lane quadrant
   static constexpr int EPI_THREADS = 128 * EPI_GROUPS;
@@ -138,9 +138,10 @@ enum : uint32_t { kTagProducerEmpty = 1, kTagMmaFull = 2, kTagMmaTmemEmpty = 3, 
 //   struct Params;                                        (trivially copyable, passed by value)
 //   static constexpr bool kUsesScratch;  if true: `uint8_t* scratch` member, EPI_SCRATCH_PER_WARP bytes of smem per warp
 //   static constexpr bool kStagesColumns;  if true: `const float* cols` member + `float column_value(const Params&, int col)`:
-//       before a tile's accumulator is awaited, each of the 256 epilogue threads fetches the value of one of the
-//       tile's columns (its global-memory latency hides behind the wait), parks it in shared memory, and `cols`
-//       points at the 32 values of the chunk being processed -- instead of every thread loading 32 per chunk
+//       before a tile's accumulator is awaited, every lane of an epilogue warp fetches the values of 4 of the warp's
+//       128 columns of the tile (the global-memory latency hides behind the wait), the warp parks them in its own
+//       strip of shared memory, and `cols` points at the 32 values of the chunk being processed -- instead of every
+//       thread loading 32 values per chunk from global memory
 //   __device__ void begin_unit(const Params&, int row, int m_tile, int split);
 //   __device__ void chunk(const Params&, int row, int col0, const uint32_t (&v)[32]);   fp32 bit patterns
 //   __device__ void end_unit(const Params&, int row, int m_tile, int slot);     slot = split * col_groups + group
@@ -366,16 +367,21 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     float* col_stage = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + 8 * Cfg::EPI_SCRATCH_PER_WARP);
     auto epi_tile = [&](int row, int t) {
       const uint32_t acc = it % Cfg::ACC_STAGES, acc_phase = (it / Cfg::ACC_STAGES) & 1u;
-      float colv = 0.f;
-      if constexpr (Epi::kStagesColumns) colv = epi.column_value(ep, t * Cfg::BN + static_cast<int>(threadIdx.x));
-      float* cols_tile = col_stage + (it & 1u) * 256;
+      float colv[Cfg::CHUNKS_PER_GROUP];
+      float* cols_warp = col_stage + warp * 128;
+      if constexpr (Epi::kStagesColumns) {
+#pragma unroll
+        for (int c = 0; c < Cfg::CHUNKS_PER_GROUP; ++c)
+          colv[c] = epi.column_value(ep, t * Cfg::BN + (group * Cfg::CHUNKS_PER_GROUP + c) * 32 + lane);
+      }
       ++it;
       mbar_wait(&tmem_full_bar[acc], acc_phase, kTagEpiTmemFull, acc);
       tc_fence_after();
       if constexpr (Epi::kStagesColumns) {
-        // buffer (it & 1) was last read two tiles ago: every epilogue thread has passed the previous tile's barrier since
-        cols_tile[threadIdx.x] = colv;
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps (threads 0..255) only
+        __syncwarp();   // every lane is done reading the previous tile's values
+#pragma unroll
+        for (int c = 0; c < Cfg::CHUNKS_PER_GROUP; ++c) cols_warp[c * 32 + lane] = colv[c];
+        __syncwarp();
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::BN +
                              group * (Cfg::CHUNKS_PER_GROUP * 32);
@@ -401,7 +407,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (CG == 1 || leader) mbar_arrive(&tmem_empty_bar[acc]);
           else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
         }
-        if constexpr (Epi::kStagesColumns) epi.cols = cols_tile + (group * Cfg::CHUNKS_PER_GROUP + c) * 32;
+        if constexpr (Epi::kStagesColumns) epi.cols = cols_warp + c * 32;
         if (!(shp.debug_flags & 1)) epi.chunk(ep, row, t * Cfg::BN + (group * Cfg::CHUNKS_PER_GROUP + c) * 32, v);
       }
     };
