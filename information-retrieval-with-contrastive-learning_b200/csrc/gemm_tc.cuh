@@ -119,7 +119,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = BN_CTA * 128;
   static constexpr int STAGE_BYTES = PARTS * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;  // 16-bit, 256-wide: 4 (CG 1) / 6 (CG 2); fp32 split: 2 / 3
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;  // 16-bit, 256-wide: 4 (CG 1) / 6 (CG 2); 192-wide: 5 / 7; fp32 split: 2 / 3
   static constexpr int BAR_BYTES = 256;
   static constexpr int EPI_SCRATCH_PER_WARP = 2560;  // 32 rows x (64 + 16 pad) bytes: staging for coalesced epilogue stores
   static constexpr int COL_STAGE_BYTES = 8 * 128 * 4;   // per epilogue warp: the values of its 128 columns of a tile (Epi::kStagesColumns)

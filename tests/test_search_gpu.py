@@ -438,10 +438,12 @@ def test_paired_scores_golden(golden_dir):
     assert abs(out.mean().item() - float(z["mean"])) < 1e-6
 
 
-def test_search_is_cuda_graph_capturable():
-    """Serving loop: the staging + scan + select launches of a small-batch search captured once in a CUDA graph
-    and replayed on new claims (no host-side planning or launches per query batch)."""
-    q, c = _data(16, 200_000, 768, torch.bfloat16, planted=True)
+@pytest.mark.parametrize("nq", [16, 600])
+def test_search_is_cuda_graph_capturable(nq):
+    """Serving loop: the staging + scan + select launches of a search captured once in a CUDA graph and replayed on new
+    claims (no host-side planning or launches per query batch).  16 claims: a single-round scan; 600 claims: a
+    multi-round scan, i.e. the round barrier and its COOPERATIVE launch inside a captured graph."""
+    q, c = _data(nq, 200_000, 768, torch.bfloat16, planted=True)
     static_q = q.clone()
     drs_b200.search(static_q, c, 10)                                # warm-up: lazy init happens outside the capture
     torch.cuda.synchronize()
@@ -449,14 +451,14 @@ def test_search_is_cuda_graph_capturable():
     with torch.cuda.graph(graph):
         s, i = drs_b200.search(static_q, c, 10)
     for seed in (1, 2):
-        q2, _ = _data(16, 200_000, 768, torch.bfloat16, planted=True, seed=seed)
-        q2 = torch.nn.functional.normalize(c[seed * 100: seed * 100 + 16].float() + 0.05 * q2.float(), dim=1).to(torch.bfloat16)
+        q2, _ = _data(nq, 200_000, 768, torch.bfloat16, planted=True, seed=seed)
+        q2 = torch.nn.functional.normalize(c[seed * 100: seed * 100 + nq].float() + 0.05 * q2.float(), dim=1).to(torch.bfloat16)
         static_q.copy_(q2)
         graph.replay()
         torch.cuda.synchronize()
         es, ei = drs_b200.search(q2, c, 10)
         assert torch.equal(i, ei) and torch.equal(s, es)
-        assert ei[:, 0].cpu().tolist() == list(range(seed * 100, seed * 100 + 16))
+        assert ei[:, 0].cpu().tolist() == list(range(seed * 100, seed * 100 + nq))
 
 
 @pytest.mark.parametrize("nq,nc,dim,k", [(64, 5000, 128, 5), (300, 40000, 768, 10), (1000, 30000, 256, 100)])
