@@ -234,6 +234,7 @@ exchange_sliced_kernel(const float* __restrict__ local_s, const long long* __res
   const int per = (nq + world - 1) / world;                                   // claims per slice
   const int bps = (per + kSlicedRowsPerBlock - 1) / kSlicedRowsPerBlock;      // claim blocks per slice
   const size_t run = static_cast<size_t>(per) * k;                            // one source's lists of one slice
+  const bool vec_in = (k & 3) == 0 && (reinterpret_cast<uintptr_t>(local_s) & 15) == 0 && (reinterpret_cast<uintptr_t>(local_i) & 15) == 0;
 
   // ---- phase 1: scatter my lists, slice by slice, into the owners' gather buffers
   for (int gb = blockIdx.x; gb < world * bps; gb += gridDim.x) {
@@ -245,9 +246,18 @@ exchange_sliced_kernel(const float* __restrict__ local_s, const long long* __res
       long long* gi = reinterpret_cast<long long*>(peers.base[dest] + par + peers.gather_i_off);
       const size_t dst = static_cast<size_t>(rank) * run + static_cast<size_t>(ql) * k;
       const size_t src = static_cast<size_t>(q) * k;
-      for (int j = lane; j < k; j += 32) {
-        gs[dst + j] = __ldcg(local_s + src + j);
-        gi[dst + j] = __ldcg(local_i + src + j);
+      if (vec_in) {         // rows are 16-byte multiples: 16-byte peer stores (4 scores / 2 ids per lane), 512 bytes per instruction
+        const uint4* ss = reinterpret_cast<const uint4*>(local_s + src);
+        const uint4* si = reinterpret_cast<const uint4*>(local_i + src);
+        uint4* ds = reinterpret_cast<uint4*>(gs + dst);
+        uint4* di = reinterpret_cast<uint4*>(gi + dst);
+        for (int j = lane; j < k / 4; j += 32) ds[j] = __ldcg(ss + j);
+        for (int j = lane; j < k / 2; j += 32) di[j] = __ldcg(si + j);
+      } else {
+        for (int j = lane; j < k; j += 32) {
+          gs[dst + j] = __ldcg(local_s + src + j);
+          gi[dst + j] = __ldcg(local_i + src + j);
+        }
       }
     }
     __syncthreads();
@@ -336,9 +346,18 @@ exchange_sliced_kernel(const float* __restrict__ local_s, const long long* __res
     const int q1 = min(min(q0 + kSlicedRowsPerBlock, (s + 1) * per), nq);
     if (q1 > q0) {
       const size_t lo = static_cast<size_t>(q0) * k, n = static_cast<size_t>(q1 - q0) * k;
-      for (size_t e = threadIdx.x; e < n; e += blockDim.x) {
-        out_scores[lo + e] = __ldcg(rs + lo + e);
-        out_ids[lo + e] = __ldcg(ri + lo + e);
+      if ((k & 3) == 0 && (reinterpret_cast<uintptr_t>(out_scores) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_ids) & 15) == 0) {
+        const uint4* ss = reinterpret_cast<const uint4*>(rs + lo);
+        const uint4* si = reinterpret_cast<const uint4*>(ri + lo);
+        uint4* ds = reinterpret_cast<uint4*>(out_scores + lo);
+        uint4* di = reinterpret_cast<uint4*>(out_ids + lo);
+        for (size_t e = threadIdx.x; e < n / 4; e += blockDim.x) ds[e] = __ldcg(ss + e);
+        for (size_t e = threadIdx.x; e < n / 2; e += blockDim.x) di[e] = __ldcg(si + e);
+      } else {
+        for (size_t e = threadIdx.x; e < n; e += blockDim.x) {
+          out_scores[lo + e] = __ldcg(rs + lo + e);
+          out_ids[lo + e] = __ldcg(ri + lo + e);
+        }
       }
     }
     __syncthreads();
