@@ -56,7 +56,9 @@ int drs_debug_max_clusters(int cluster_size, int* out);
  * (preprocessing/drqa/retriever/tfidf_doc_ranker.py:60-75), batched over claims like
  * batch_closest_docs (:77-84).
  *
- *   queries  device [nq, dim]   dtype DRS_BF16 / DRS_F16 (tcgen05 path, fp32 accumulate) or DRS_F32 (exact FFMA path)
+ *   queries  device [nq, dim]   dtype DRS_BF16 / DRS_F16 (tcgen05, fp32 accumulate) or DRS_F32 (the exact-comparison path: fp32
+ *                                operands on tcgen05 as a 3 x TF32 split, <= 4e-6 relative; FFMA kernel when dim % 4 != 0 or
+ *                                "search.fp32_mode" = 1)
  *   corpus   device [nc, dim]   same dtype
  *   out_scores device [nq, k] fp32, descending;  out_ids device [nq, k] int64 = row + id_base
  *   ties are broken by the lower row index; when nc < k the tail is (-inf, -1).

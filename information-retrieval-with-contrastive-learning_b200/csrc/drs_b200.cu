@@ -61,6 +61,7 @@ struct Options {
   int round_barrier = 1;
   int seed_thresholds = 1;
   int symmetric_grad = 2;   // InfoNCE backward: 0 full H, 1 upper tiles computed + mirrored stores, 2 upper tiles only (dF reads transposed)
+  int fp32_tile = 128;     // B-tile width of the fp32 tensor-core scan: 128 (two accumulator stages: 0.66 ms on config 0) or 256 (one: 0.73 ms)
   int m_block = 0;         // search: A tiles per super-block of the unit order: 0 auto (= clusters), -1 off
   int df_tile = 0;         // InfoNCE dF = H F GEMM tile width: 0 auto, 256, 192
   int fp32_mode = 0;       // DRS_F32 search: 0 = 3 x TF32 on tcgen05 (when dim % 4 == 0 and 16-byte aligned), 1 = FFMA kernel
@@ -230,6 +231,7 @@ struct SearchPlan {
   int seed_group;     // rows certified by one published value (epilogues.cuh)
   int seed_chunks;    // values a unit publishes: seed_chunks * seed_group <= entries selected per pass
   bool f32_tc;        // DRS_F32 on the tensor cores (3 x TF32): claims and corpus are split into hi + lo first
+  int f32_bn;         // B-tile width of the fp32 tensor-core scan: 256 (one accumulator stage) or 128 (two)
   bool f32_prepared;  // the split of this call has been enqueued (multi-pass searches split once)
   size_t f32_a_bytes; // one padded [a_rows, dim] fp32 copy of the claims (two are kept: hi, lo)
   size_t f32_b_bytes; // the corpus residual [nc, dim] fp32
@@ -266,7 +268,8 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
     ctas = std::max(cg, ctas - ctas % cg);
     p->cg = cg;
     p->grid = ctas;
-    p->shape = plan_shape(nq, nc, p->f32_tc ? (dim + 31) / 32 : (dim + 63) / 64, 128 * cg, 256, ctas / cg, g_opt.splits, kTcColGroups);
+    p->f32_bn = (p->f32_tc && g_opt.fp32_tile != 256) ? 128 : 256;
+    p->shape = plan_shape(nq, nc, p->f32_tc ? (dim + 31) / 32 : (dim + 63) / 64, 128 * cg, p->f32_tc ? p->f32_bn : 256, ctas / cg, g_opt.splits, kTcColGroups);
     p->shape.f16_operands = dtype == DRS_F16;
     p->shape.m_block = g_opt.m_block < 0 ? 0 : (g_opt.m_block > 0 ? g_opt.m_block : ctas / cg);   // A super-blocks (gemm_tc.cuh::unit_to_tile)
   } else if (dtype == DRS_F32) {
@@ -423,18 +426,18 @@ int launch_gemm_simt(const float* a, long long lda, const float* b, long long ld
   return DRS_OK;
 }
 
-template <int CG, int KCAP, int PREC = 0>
+template <int CG, int KCAP, int PREC = 0, int BN = 256>
 int launch_search_tc(const SearchPlan& p, const void* queries, const void* corpus, int dim, uint64_t* ws, int k_pass,
                      const uint64_t* bound, const float* col_bias, uint32_t* seeds, cudaStream_t st,
                      const void* queries_lo = nullptr, const void* corpus_lo = nullptr) {
   if (col_bias != nullptr) {
     using Epi = drs::TopKEpilogue<KCAP, true>;
     typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, col_bias, 2.0f, seeds, p.seed_slots, p.seed_group, p.seed_chunks};
-    return launch_gemm_tc<CG, Epi, 256, PREC>(queries, corpus, dim, p.shape, p.grid, ep, st, p.a_rows, 0, 0, queries_lo, corpus_lo);
+    return launch_gemm_tc<CG, Epi, BN, PREC>(queries, corpus, dim, p.shape, p.grid, ep, st, p.a_rows, 0, 0, queries_lo, corpus_lo);
   }
   using Epi = drs::TopKEpilogue<KCAP>;
   typename Epi::Params ep{ws, p.shape.rows_a, p.shape.rows_b, num_slots(p.shape), k_pass, bound, nullptr, 1.0f, seeds, p.seed_slots, p.seed_group, p.seed_chunks};
-  return launch_gemm_tc<CG, Epi, 256, PREC>(queries, corpus, dim, p.shape, p.grid, ep, st, p.a_rows, 0, 0, queries_lo, corpus_lo);
+  return launch_gemm_tc<CG, Epi, BN, PREC>(queries, corpus, dim, p.shape, p.grid, ep, st, p.a_rows, 0, 0, queries_lo, corpus_lo);
 }
 
 template <int KCAP>
@@ -563,6 +566,7 @@ int drs_set_option(const char* name, int value) {
   else if (!strcmp(name, "search.fp32_mode")) g_opt.fp32_mode = value;
   else if (!strcmp(name, "infonce.df_tile")) g_opt.df_tile = value;
   else if (!strcmp(name, "search.m_block")) g_opt.m_block = value;
+  else if (!strcmp(name, "search.fp32_tile")) g_opt.fp32_tile = value;
   else if (!strcmp(name, "debug.coop_fallbacks")) g_opt.coop_fallbacks = value;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;
@@ -583,6 +587,7 @@ int drs_get_option(const char* name, int* value) {
   else if (!strcmp(name, "search.fp32_mode")) *value = g_opt.fp32_mode;
   else if (!strcmp(name, "infonce.df_tile")) *value = g_opt.df_tile;
   else if (!strcmp(name, "search.m_block")) *value = g_opt.m_block;
+  else if (!strcmp(name, "search.fp32_tile")) *value = g_opt.fp32_tile;
   else if (!strcmp(name, "debug.coop_fallbacks")) *value = g_opt.coop_fallbacks;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;
@@ -652,9 +657,13 @@ int scan_pass(SearchPlan& p, const void* queries, const void* corpus, int dim, v
       DRS_CUDA(cudaGetLastError());
       p.f32_prepared = true;
     }
-#define DRS_F32TC(CGV, KC) launch_search_tc<CGV, KC, 1>(p, a_hi, corpus, dim, ws, k_pass, bound, col_bias, seeds, st, a_lo, b_lo)
-    if (p.cg == 1) return p.kcap == 16 ? DRS_F32TC(1, 16) : DRS_F32TC(1, 32);
-    return p.kcap == 16 ? DRS_F32TC(2, 16) : DRS_F32TC(2, 32);
+#define DRS_F32TC(CGV, KC, BNV) launch_search_tc<CGV, KC, 1, BNV>(p, a_hi, corpus, dim, ws, k_pass, bound, col_bias, seeds, st, a_lo, b_lo)
+    if (p.f32_bn == 128) {   // 128-wide tiles: two accumulator stages (main + correction each) fit TMEM, the epilogue overlaps the MMAs
+      if (p.cg == 1) return p.kcap == 16 ? DRS_F32TC(1, 16, 128) : DRS_F32TC(1, 32, 128);
+      return p.kcap == 16 ? DRS_F32TC(2, 16, 128) : DRS_F32TC(2, 32, 128);
+    }
+    if (p.cg == 1) return p.kcap == 16 ? DRS_F32TC(1, 16, 256) : DRS_F32TC(1, 32, 256);
+    return p.kcap == 16 ? DRS_F32TC(2, 16, 256) : DRS_F32TC(2, 32, 256);
 #undef DRS_F32TC
   }
   if (is_16bit(p.dtype)) {

@@ -7,8 +7,9 @@ products); its live score+select signature is ``TfidfDocRanker.closest_docs(quer
 (preprocessing/drqa/retriever/tfidf_doc_ranker.py:60-84).  ``DenseIndex`` keeps those names,
 argument meaning and return shapes; ``search`` is the tensor-level call underneath.
 
-All arithmetic runs in the CUDA extension (csrc/): a tcgen05 bf16 score GEMM (or an fp32 FFMA
-GEMM for exact comparison) with the top-k select fused into its epilogue.  There is no CPU path.
+All arithmetic runs in the CUDA extension (csrc/): a tcgen05 score GEMM -- bf16 / fp16 operands, or fp32
+operands as a 3 x TF32 split for exact comparison (an FFMA kernel is its checker) -- with the top-k select
+fused into its epilogue.  There is no CPU path.
 """
 from __future__ import annotations
 
@@ -50,7 +51,7 @@ def search(queries: torch.Tensor, corpus: torch.Tensor, k: int, *, id_base: int 
     """Top-k corpus rows per query by dot product.
 
     queries [nq, D], corpus [Nc, D]: CUDA, row-major, same dtype (bf16 or fp16 -> tcgen05 path, fp32
-    accumulation, scores within 2e-2 relative of fp32; fp32 -> exact FFMA path, 1e-5).  Rows are expected to be
+    accumulation, scores within 2e-2 relative of fp32; fp32 -> 3 x TF32 on tcgen05 / FFMA kernel, 1e-5).  Rows are expected to be
     L2-normalised the way ``seq2vec`` does (src/contrastor/contrastive_module.py:111), so the dot
     product is the cosine; nothing here depends on that.
 
@@ -129,7 +130,7 @@ def flat_l2_search(x: torch.Tensor, centroids: torch.Tensor, k: int = 1, *, id_b
     """Exact squared-L2 nearest neighbours: what ``faiss.GpuIndexFlatL2.search(x, k)`` returns at
     src/contrastor/utils.py:64-67 (the k-means assignment of ``run_kmeans``).
 
-    x [n, D], centroids [Nc, D]: CUDA, same dtype (fp32 -> exact FFMA path like faiss's
+    x [n, D], centroids [Nc, D]: CUDA, same dtype (fp32 -> the exact path (3 x TF32 on tcgen05) like faiss's
     ``useFloat16 = False`` at utils.py:44; bf16 -> tcgen05 path).  Returns (D fp32 [n, k'] ascending
     squared distances, I int64 [n, k']), k' = min(k, Nc), ties -> lower index.
     PARITY UNPINNED against faiss itself (unpinned, not vendored, not installed)."""
