@@ -79,6 +79,16 @@ def test_fp32_exact_parity(nq, nc, dim, k, mode):
     _check(q, c, k, s, i, score_rtol=1e-5, gap=5e-6)
 
 
+@pytest.mark.parametrize("dtype,dim", [(torch.bfloat16, 2048), (torch.bfloat16, 4096), (torch.float32, 2048), (torch.bfloat16, 8),
+                                       (torch.float32, 4)])
+def test_extreme_embedding_widths(dtype, dim):
+    """Very wide (64 K blocks per tile) and very narrow rows on both tensor-core paths."""
+    q, c = _data(200, 30000, dim, dtype, planted=dim >= 64)
+    s, i = drs_b200.search(q, c, 10)
+    tol = (1e-5, 5e-6) if dtype == torch.float32 else (2e-2, 1e-4)
+    _check(q, c, 10, s, i, score_rtol=tol[0], gap=tol[1])
+
+
 def test_fp32_tensor_core_path_agrees_with_the_ffma_checker():
     """The two fp32 arithmetic paths on the same data: scores within 4e-6 relative of each other (measured worst case
     of the 3 x TF32 split against float64: 3.8e-6), ids identical wherever the FFMA path's gap exceeds 1e-5."""
