@@ -17,8 +17,13 @@
 namespace drs {
 
 template <typename T> struct RowVec;
+// (load = raw + cvt; the gather keeps many raw 16-byte loads in flight and converts afterwards)
 template <> struct RowVec<float> {
   static constexpr int W = 4;  // elements per 16-byte load
+  static __device__ __forceinline__ uint4 raw(const float* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ void cvt(const uint4& t, float (&v)[4]) {
+    v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+  }
   static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
     const float4 t = __ldg(reinterpret_cast<const float4*>(p));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -26,6 +31,15 @@ template <> struct RowVec<float> {
 };
 template <> struct RowVec<__nv_bfloat16> {
   static constexpr int W = 8;
+  static __device__ __forceinline__ uint4 raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ void cvt(const uint4& t, float (&v)[8]) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
     const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
@@ -39,6 +53,16 @@ template <> struct RowVec<__nv_bfloat16> {
 
 template <> struct RowVec<__half> {
   static constexpr int W = 8;
+  static __device__ __forceinline__ uint4 raw(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ void cvt(const uint4& t, float (&v)[8]) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
   static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
     const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
@@ -86,16 +110,53 @@ rerank_kernel(const T* __restrict__ queries, const T* __restrict__ corpus, const
   for (int d = threadIdx.x; d < dim; d += blockDim.x) qs[d] = static_cast<float>(queries[static_cast<size_t>(q) * dim + d]);
   __syncthreads();
   const long long* my = cand + static_cast<size_t>(q) * m;
-  for (int c = warp; c < m; c += nwarps) {
-    const long long id = __ldg(my + c);
-    uint64_t key = 0ull;
-    if (id >= 0 && id < nc) {
-      const float s = warp_row_dot<T, VEC>(corpus + static_cast<size_t>(id) * dim, qs, dim, lane);
+  if constexpr (VEC) {
+    // Four candidates per warp at a time (8 lanes each: 8 x 16 bytes = one 128-byte line per step) and up to twelve
+    // independent 16-byte loads in flight per lane (a whole 768-wide bf16 row): one candidate per warp with three dependent steps left the
+    // gather latency-bound at 3.1 TB/s (47 % of the copy bandwidth) for 10 000 claims x 100 candidates x 768.
+    constexpr int W = RowVec<T>::W;
+    constexpr int U = 12;
+    const int sub = lane >> 3, l8 = lane & 7;
+    const int nvec = dim / W;
+    for (int base = warp * 4; base < m; base += nwarps * 4) {
+      const int c = base + sub;
+      const long long id = c < m ? __ldg(my + c) : -1ll;
+      const bool ok = id >= 0 && id < nc;
+      const T* row = corpus + static_cast<size_t>(ok ? id : 0) * dim;
+      float acc = 0.f;
+      for (int v0 = l8; v0 < nvec; v0 += 8 * U) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int v = v0 + 8 * u;
+          raw[u] = (ok && v < nvec) ? RowVec<T>::raw(row + static_cast<size_t>(v) * W) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int v = min(v0 + 8 * u, nvec - 1);
+          float x[W];
+          RowVec<T>::cvt(raw[u], x);
+#pragma unroll
+          for (int i = 0; i < W; ++i) acc = fmaf(x[i], qs[v * W + i], acc);
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       // a NaN score is never a candidate, exactly as in the search epilogue (`s > thr` is false for NaN) and as
       // numpy's argpartition / argsort order NaN last in closest_docs (tfidf_doc_ranker.py:70-71)
-      if (s == s) key = make_key(s, static_cast<uint32_t>(id));
+      if (l8 == 0 && c < m) keys[c] = (ok && acc == acc) ? make_key(acc, static_cast<uint32_t>(id)) : 0ull;
     }
-    if (lane == 0) keys[c] = key;
+  } else {
+    for (int c = warp; c < m; c += nwarps) {
+      const long long id = __ldg(my + c);
+      uint64_t key = 0ull;
+      if (id >= 0 && id < nc) {
+        const float s = warp_row_dot<T, VEC>(corpus + static_cast<size_t>(id) * dim, qs, dim, lane);
+        if (s == s) key = make_key(s, static_cast<uint32_t>(id));
+      }
+      if (lane == 0) keys[c] = key;
+    }
   }
   __syncthreads();
   if (warp != 0) return;
