@@ -6,8 +6,8 @@ Mirror of src/contrastor/contrastive_loss.py: same class names, constructor argu
 hold no parameters or buffers, so ``RetrievalModelWrapper.state_dict()`` is unchanged
 (checkpoints load with strict=True, src/model.py:93).
 
-``loss_config['precision']`` (extension): 'auto' (default) = 'bf16' when the shapes allow it, else
-'fp32'; 'bf16' = inputs rounded to bf16, tcgen05 MMA, fp32 accumulation and fp32 softmax; 'fp32' = FFMA
+``loss_config['precision']`` (extension): 'auto' (default) = 'bf16' when the shapes allow it and the embeddings are
+at least 64 wide, else 'fp32'; 'bf16' = inputs rounded to bf16, tcgen05 MMA, fp32 accumulation and fp32 softmax; 'fp32' = FFMA
 path for exact comparison.
 
 NUMERICS DIFFER FROM THE REFERENCE ON THE DEFAULT PATH.  The reference computes the logits with an fp32
@@ -44,7 +44,10 @@ def _pick_precision(requested, n, dim, klen):
     engine pads the pitch and lets the tensor maps zero-fill), only dim % 8 == 0 remains."""
     bf16_ok = dim % 8 == 0 and n % 4 == 0 and klen % 8 == 0
     if requested in (None, "auto"):
-        return _lib.DRS_BF16 if bf16_ok else _lib.DRS_F32
+        # narrow embeddings stay in fp32: with T = 0.05 the bf16 rounding of a 16-wide dot product moves single gradient
+        # rows by ~3 % (tools/gpu_loss_emulation_check.py: the kernel matches a bf16 emulation to 1e-4, the emulation is
+        # 2.6e-2 off the fp32 result at dim = 16, 7e-3 at dim = 64) -- and there is nothing to gain at that size
+        return _lib.DRS_BF16 if (bf16_ok and dim >= 64) else _lib.DRS_F32
     if requested == "bf16":
         if not bf16_ok:
             raise RuntimeError("bf16 path needs dim % 8 == 0 (and, for the in-batch form, batch % 4 == 0 and queue_len % 8 == 0)")
