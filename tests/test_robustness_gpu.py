@@ -106,6 +106,16 @@ def test_sharded_index_row_ids_round_trip():
         shard.get_doc_id(5)
 
 
+def test_randomised_stress_of_multi_round_scans_and_losses():
+    """tools/gpu_stress.py with a fixed seed: 60 search shapes whose claims' units run over several rounds (threshold
+    seeds, round barrier, adaptive passes, planted duplicates across units) and 24 InfoNCE shapes (symmetric H, transposed
+    reads, queues), each against an exact fp32 / fp64 computation on the GPU."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_stress.py"), "60", "24", "11"], capture_output=True,
+                         text=True, timeout=800)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "search: 60 / 60 ok" in out.stdout and "loss: 24 / 24 ok" in out.stdout
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
