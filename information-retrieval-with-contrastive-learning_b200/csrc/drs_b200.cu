@@ -61,6 +61,7 @@ struct Options {
   int round_barrier = 1;
   int seed_thresholds = 1;
   int symmetric_grad = 2;   // InfoNCE backward: 0 full H, 1 upper tiles computed + mirrored stores, 2 upper tiles only (dF reads transposed)
+  int tma_store = 1;       // InfoNCE backward: the gradient-of-logits tiles leave through TMA stores
   int fp32_tile = 128;     // B-tile width of the fp32 tensor-core scan: 128 (two accumulator stages: 0.66 ms on config 0) or 256 (one: 0.73 ms)
   int m_block = 0;         // search: A tiles per super-block of the unit order: 0 auto (= clusters), -1 off
   int df_tile = 0;         // InfoNCE dF = H F GEMM tile width: 0 auto, 256, 192
@@ -165,6 +166,20 @@ int make_tmap_f32(CUtensorMap* m, const void* base, int64_t rows, int dim, int b
   return DRS_OK;
 }
 
+// a bf16 OUTPUT matrix [rows, cols] (row pitch in elements) for the epilogue's TMA stores: box 32 x 32, 64-byte swizzle
+int make_tmap_out_bf16(CUtensorMap* m, void* base, int64_t rows, int64_t cols, int64_t pitch) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(DRS_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(pitch) * 2};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DRS_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (CUresult %d)", static_cast<int>(r));
+  return DRS_OK;
+}
+
 // ------------------------------------------------------------------ work decomposition
 // units = num_m_tiles * splits, dealt round-robin to `groups` persistent clusters; a unit is `tiles_per_split`
 // consecutive B tiles against one A tile.
@@ -205,6 +220,7 @@ drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int 
   s.active = nullptr;
   s.f16_operands = 0;
   s.m_block = 0;
+  s.epi_tma_store = 0;
   s.a_sym = 0;
   s.skip_below_diagonal = 0;
   return s;
@@ -348,6 +364,13 @@ int launch_gemm_tc(const void* a, const void* b, int kdim, drs::GemmShape shp, i
     if (int rc = make_tmap_bf16(&tb, b, shp.rows_b, kdim, Cfg::BN_CTA, shp.f16_operands != 0, pitch_b)) return rc;
     ta_lo = ta;
     tb_lo = tb;
+    if (shp.epi_tma_store) {   // the epilogue's output matrix (GradLogitEpilogue: ep.out, rows_a x rows_b, pitch ld_out)
+      if constexpr (Epi::kUsesScratch) {
+        if (int rc = make_tmap_out_bf16(&tb_lo, ep.out, ep.rows_a, ep.rows_b, ep.ld_out)) return rc;
+      } else {
+        return fail(DRS_ERR_INVALID, "internal: epi_tma_store needs an epilogue with an output matrix");
+      }
+    }
     if (shp.a_sym) {   // the transposed view of the (square, symmetric) A operand: 64 x 64 boxes of the same matrix
       if (CG != 2 || shp.rows_a != kdim) return fail(DRS_ERR_INVALID, "internal: a_sym needs the CTA-pair kernel and a square A");
       if (int rc = make_tmap_bf16(&ta_lo, a, rows_a_map, kdim, 64, shp.f16_operands != 0, pitch_a)) return rc;
@@ -567,6 +590,7 @@ int drs_set_option(const char* name, int value) {
   else if (!strcmp(name, "infonce.df_tile")) g_opt.df_tile = value;
   else if (!strcmp(name, "search.m_block")) g_opt.m_block = value;
   else if (!strcmp(name, "search.fp32_tile")) g_opt.fp32_tile = value;
+  else if (!strcmp(name, "infonce.tma_store")) g_opt.tma_store = value;
   else if (!strcmp(name, "debug.coop_fallbacks")) g_opt.coop_fallbacks = value;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;
@@ -588,6 +612,7 @@ int drs_get_option(const char* name, int* value) {
   else if (!strcmp(name, "infonce.df_tile")) *value = g_opt.df_tile;
   else if (!strcmp(name, "search.m_block")) *value = g_opt.m_block;
   else if (!strcmp(name, "search.fp32_tile")) *value = g_opt.fp32_tile;
+  else if (!strcmp(name, "infonce.tma_store")) *value = g_opt.tma_store;
   else if (!strcmp(name, "debug.coop_fallbacks")) *value = g_opt.coop_fallbacks;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", name);
   return DRS_OK;

@@ -39,6 +39,8 @@ struct GemmShape {
   unsigned int* round_counter;  // zeroed device counter for the per-round producer barrier, or nullptr
   const unsigned int* active;   // optional: the whole launch is a no-op when *active == 0 (adaptive k > 32 passes)
   int f16_operands;             // 0: bf16 operands, 1: IEEE half operands (same kind::f16 MMA, other instruction descriptor)
+  int epi_tma_store;            // the epilogue functor stores its tiles with TMA (cp.async.bulk.tensor) through `tmap_b_lo`,
+                                // which then describes the OUTPUT matrix (box 32 x 32, 64-byte swizzle); PREC == 0 only
   int a_sym;                    // CG == 2, PREC == 0: A is a SYMMETRIC square matrix of which only the 256 x 256 tiles on and
                                 // above the diagonal are stored (the gradient-of-logits matrix H of the InfoNCE backward):
                                 // K blocks left of A tile m's diagonal tile (kb < 4 m) are read TRANSPOSED from the stored
@@ -121,7 +123,7 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN_CTA * 128;
   static constexpr int STAGE_BYTES = PARTS * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;  // 16-bit, 256-wide: 4 (CG 1) / 6 (CG 2); 192-wide: 5 / 7; fp32 split: 2 / 3
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 1024;  // (a 1024-byte slot keeps the epilogue staging areas behind it 512-byte aligned for swizzled TMA stores)
   static constexpr int EPI_SCRATCH_PER_WARP = 2560;  // 32 rows x (64 + 16 pad) bytes: staging for coalesced epilogue stores
   static constexpr int COL_STAGE_BYTES = 8 * 128 * 4;   // per epilogue warp: the values of its 128 columns of a tile (Epi::kStagesColumns)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 8 * EPI_SCRATCH_PER_WARP + COL_STAGE_BYTES + 1024;  // + alignment slack
@@ -364,8 +366,10 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int group = warp >> 2;       // which column group of every tile this warp owns
     const int row_in_tile = quad * 32 + lane;
     Epi epi;
-    if constexpr (Epi::kUsesScratch)  // a private staging area per epilogue warp, behind the barriers
+    if constexpr (Epi::kUsesScratch) {  // a private staging area per epilogue warp, behind the barriers
       epi.scratch = smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + warp * Cfg::EPI_SCRATCH_PER_WARP;
+      epi.out_map = (PREC == 0 && shp.epi_tma_store) ? &tmap_b_lo : nullptr;
+    }
     uint32_t it = 0;
     float* col_stage = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + 8 * Cfg::EPI_SCRATCH_PER_WARP);
     auto epi_tile = [&](int row, int t) {
@@ -434,6 +438,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         epi.end_unit(ep, row, m, s * Cfg::EPI_GROUPS + group);
       }
     }
+    if constexpr (Epi::kUsesScratch) epi.finish();   // e.g. outstanding bulk stores must have left shared memory
   }
 
   __syncwarp();  // reconverge the single-thread roles before the aligned barriers below

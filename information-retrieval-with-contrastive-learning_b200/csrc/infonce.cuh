@@ -144,6 +144,7 @@ struct GradLogitEpilogue {
   static constexpr bool kUsesScratch = sizeof(OutT) == 2;
   static constexpr bool kStagesColumns = sizeof(OutT) == 2;   // mode 0 needs the LSE of every COLUMN: staged per tile by the kernel
   uint8_t* scratch = nullptr;  // per-warp smem staging (tensor-core kernel only), see store32_coalesced
+  const CUtensorMap* out_map = nullptr;  // when set: chunks leave through TMA stores (store32_tma)
   const float* cols = nullptr; // the 32 column LSEs of the current chunk in shared memory (tensor-core kernel only)
   float li, li2, c;
 
@@ -175,6 +176,39 @@ struct GradLogitEpilogue {
     } else {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
+    }
+  }
+
+  // The same staging, handed to the TMA: the warp writes its 32 x 32 bf16 block into shared memory in the 64-byte
+  // swizzle pattern (16-byte chunk j of row r at chunk j ^ ((r >> 1) & 3): conflict-free), one lane issues a bulk
+  // tensor store (rows past the end of the matrix are clipped by the tensor map) and the warp moves on; the wait for
+  // the TMA to have READ the block happens just before the next chunk is staged, a chunk's worth of arithmetic later.
+  // Replaces 4 LDS + 4 STG + their address arithmetic per chunk and takes the store latency off the warp.
+  __device__ __forceinline__ void store32_tma(int row, int col0, const float (&h)[32]) const {
+    const int lane = threadIdx.x & 31;
+    const uint32_t base = smem_u32(scratch);
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+    const uint32_t mine = base + lane * 64;
+    const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      __nv_bfloat162 t0 = __floats2bfloat162_rn(h[j + 0], h[j + 1]);
+      __nv_bfloat162 t1 = __floats2bfloat162_rn(h[j + 2], h[j + 3]);
+      __nv_bfloat162 t2 = __floats2bfloat162_rn(h[j + 4], h[j + 5]);
+      __nv_bfloat162 t3 = __floats2bfloat162_rn(h[j + 6], h[j + 7]);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(mine + (((j >> 3) ^ sw) << 4)),
+                   "r"(*reinterpret_cast<uint32_t*>(&t0)), "r"(*reinterpret_cast<uint32_t*>(&t1)),
+                   "r"(*reinterpret_cast<uint32_t*>(&t2)), "r"(*reinterpret_cast<uint32_t*>(&t3))
+                   : "memory");
+    }
+    fence_proxy_async_smem();   // generic-proxy writes -> visible to the async proxy (TMA)
+    __syncwarp();
+    if (lane == 0) tma_store_2d(out_map, scratch, col0, row - lane);
+  }
+  __device__ __forceinline__ void finish() const {
+    if constexpr (kUsesScratch) {
+      if (out_map != nullptr && (threadIdx.x & 31) == 0) tma_store_wait_all();
     }
   }
 
@@ -287,6 +321,10 @@ struct GradLogitEpilogue {
         }
         if (p.debug & 8) return;
         if constexpr (kUsesScratch) {
+          if (staged && out_map != nullptr && p.mirror_rows == 0) {
+            store32_tma(row, col0, h);
+            return;
+          }
           if (staged) {
             store32_coalesced(p, row, col0, h);
             // (row - lane) / mirror_rows is the A tile of the whole warp: the condition is warp-uniform
