@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="fever_sentences_25M", choices=sorted(WORKLOADS))
+    ap.add_argument("--regime-warm-s", type=float, default=1.5, dest="regime_warm_s",
+                    help="seconds of continuous running before each small-batch sweep row is timed (steady-state clocks)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (N=1 only runs it)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for the baseline sample")
     ap.add_argument("--no-extras", action="store_true",
@@ -469,13 +471,20 @@ def run_b200(args):
     #      corpus pass, intensity = B flop/byte, HBM-bound below the ridge (~212).  Same corpus, same call.
     regimes = []
     if not args.no_extras:
-        # measured BEFORE the headline loops: those run the chip at its power cap for seconds, and millisecond-scale
-        # measurements taken right after them inherit the throttled clocks (reported separately from `value`)
+        # every row is timed in ITS OWN steady state (warmed for --regime-warm-s seconds of continuous running first)
         for bq in (1, 16, 64, 128, 256, 384, 512, 1024, 2048):
             qs = queries[:bq].contiguous()
             rprof = []
-            for _ in range(3):
+            # warm each row for ~1.5 s first: the board reaches its 1 kW cap only after about a second of continuous
+            # running (even a plain read of the corpus settles at ~950 W), and the clocks a short window sees from a
+            # cool chip are not the ones a serving loop gets (profiles/r02_steady_probe.log)
+            t_warm = time.perf_counter()
+            n_warm = 0
+            while n_warm < 3 or time.perf_counter() - t_warm < args.regime_warm_s:
                 index.search(qs, k)
+                n_warm += 1
+                if n_warm % 8 == 0:
+                    torch.cuda.synchronize()
             reps = 20 if bq <= 256 else 10
             sampler = ClockSampler(local_rank)
             sampler.period = 0.005
@@ -637,6 +646,8 @@ def run_b200(args):
             line["small_batch_regime"] = regimes
             line["small_batch_regime_note"] = (f"hbm_frac = algorithmic bytes / scan time / {peaks['hbm_gbs']:.0f} GB/s, the measured "
                                                "copy bandwidth (read + write); a read-only stream can exceed it, so hbm_frac > 1 is possible.  "
+                                               f"Each row is timed after {args.regime_warm_s:.1f} s of continuous running at that claim count (steady-state clocks: the board "
+                                               "reaches its 1 kW cap after ~1 s even for a plain read of the corpus, profiles/r02_steady_probe.log).  "
                                                "Near the ridge (256..1024 claims per pass) HBM and the tensor pipes are both busy and the 1 kW power cap "
                                                "pulls the SM clock far below the 1335 MHz the sustained cuBLAS peak was measured at (median NVML sm_mhz and power_w "
                                                "per row -- instantaneous readings, noisy; profiles/r02_ridge_b256_kernel_metrics.json has ncu's clock for one such launch)")
