@@ -485,7 +485,9 @@ def run_b200(args):
                 n_warm += 1
                 if n_warm % 8 == 0:
                     torch.cuda.synchronize()
-            reps = 20 if bq <= 256 else 10
+            torch.cuda.synchronize()
+            per_ms = (time.perf_counter() - t_warm) * 1e3 / n_warm
+            reps = max(10, min(200, int(600.0 / max(per_ms, 0.05))))     # a ~0.6 s window: averages over the governor's swings
             sampler = ClockSampler(local_rank)
             sampler.period = 0.005
             with sampler:
