@@ -478,15 +478,14 @@ def run_b200(args):
             # warm each row for ~1.5 s first: the board reaches its 1 kW cap only after about a second of continuous
             # running (even a plain read of the corpus settles at ~950 W), and the clocks a short window sees from a
             # cool chip are not the ones a serving loop gets (profiles/r02_steady_probe.log)
-            t_warm = time.perf_counter()
-            n_warm = 0
-            while n_warm < 3 or time.perf_counter() - t_warm < args.regime_warm_s:
+            # (the number of warm-up searches is agreed between the ranks: every search on a sharded index is a
+            #  collective step, so a per-rank time-based loop would leave one rank waiting for a search that never comes)
+            per_ms = timed_loop(lambda: index.search(qs, k), 3) / 3
+            n_warm = max(3, min(2000, int(args.regime_warm_s * 1e3 / max(per_ms, 0.05))))
+            for it in range(n_warm):
                 index.search(qs, k)
-                n_warm += 1
-                if n_warm % 8 == 0:
+                if it % 8 == 7:
                     torch.cuda.synchronize()
-            torch.cuda.synchronize()
-            per_ms = (time.perf_counter() - t_warm) * 1e3 / n_warm
             reps = max(10, min(200, int(600.0 / max(per_ms, 0.05))))     # a ~0.6 s window: averages over the governor's swings
             sampler = ClockSampler(local_rank)
             sampler.period = 0.005
