@@ -259,12 +259,15 @@ def test_small_batch_bandwidth_regime_parity(nq):
     _check(q, c, 10, s, i, score_rtol=2e-2, gap=1e-4)
 
 
-def test_full_size_properties_config2():
-    """BASELINE config 1 at full size (10k claims x 5.4M x 768 bf16, top-10): size-independent
-    properties instead of an oracle pass -- planted neighbours are found first, rows are sorted,
-    ids are unique and in range, returned scores match a recomputation of those exact pairs, and
-    sharding + merge is idempotent with the single pass."""
-    nq, nc, dim, k = 10000, 5_400_000, 768, 10
+@pytest.mark.parametrize("nq,nc,k", [(10000, 5_400_000, 10),      # BASELINE configs[1]
+                                      (10000, 25_000_000, 10),     # configs[2], the metric's config (38.4 GB resident)
+                                      (65536, 675_000, 100)])      # configs[4]: one GPU's share of 5.4M docs / 8
+def test_full_size_properties(nq, nc, k):
+    """BASELINE configs at full size (x 768 bf16): size-independent properties instead of an oracle pass --
+    planted neighbours are found first, rows are sorted, ids are unique and in range, returned scores match a
+    recomputation of those exact pairs, a slice agrees with the oracle, the search is idempotent, and sharding + merge
+    gives the single-pass result bit for bit."""
+    dim = 768
     g = torch.Generator(device=DEV).manual_seed(1337)
     c = torch.empty(nc, dim, dtype=torch.bfloat16, device=DEV)
     for r0 in range(0, nc, 1 << 20):
@@ -277,9 +280,10 @@ def test_full_size_properties_config2():
     assert torch.all(s[:, :-1] >= s[:, 1:])
     assert int(i.min()) >= 0 and int(i.max()) < nc
     assert all(len(set(r)) == k for r in i[:256].cpu().tolist())
-    rec = (q.float()[:, None, :] * c[i.reshape(-1)].float().reshape(nq, k, dim)).sum(-1)
-    torch.testing.assert_close(s, rec, rtol=2e-2, atol=1e-4)
-    # a 512-claim slice against the oracle over a 200k-row window that contains each planted row's shard
+    m = 1024                                                        # recompute the returned pairs of the first m claims
+    rec = (q[:m].float()[:, None, :] * c[i[:m].reshape(-1)].float().reshape(m, k, dim)).sum(-1)
+    torch.testing.assert_close(s[:m], rec, rtol=2e-2, atol=1e-4)
+    # a claim slice against the oracle over a 200k-row window that contains each planted row
     win = c[:200000]
     sub = (planted < 200000).nonzero().flatten()[:64]
     if len(sub):
@@ -287,6 +291,8 @@ def test_full_size_properties_config2():
         rv, ri = dense_topk.search(q[sub].cpu(), win.cpu(), k)
         assert torch.equal(si.cpu()[:, 0], ri[:, 0])
         torch.testing.assert_close(sv.cpu(), rv, rtol=2e-2, atol=1e-4)
+    s2, i2 = drs_b200.search(q, c, k)                               # idempotent
+    assert torch.equal(i2, i) and torch.equal(s2, s)
     ss, ii = [], []
     for r in range(4):
         lo, hi = drs_b200.shard_bounds(nc, r, 4)
