@@ -609,9 +609,10 @@ def run_b200(args):
             traffic = json.load(open(tpath)).get(f"{args.workload}@{world}")
         except Exception:  # noqa: BLE001
             traffic = None
-    traffic_note = ("dram bytes per scan launch from the committed ncu capture (profiles/); above the algorithmic bytes because 74 "
-                    "clusters cover 1.85 corpus splits per round (40 claim tiles do not divide 74): each split is streamed in ~1.85 "
-                    "rounds; ~240 GB/s, 4 % of HBM bandwidth, in a tensor-bound kernel") if traffic else None
+    traffic_note = ((f"dram bytes per scan launch ({traffic / bytes_alg:.2f} x the algorithmic bytes) from the committed ncu capture of this "
+                     "rank's shard size (profiles/); above the algorithmic bytes because 74 clusters cover 1.85 corpus splits per "
+                     "round (40 claim tiles do not divide 74): each split is streamed in ~1.85 rounds; ~240 GB/s, 4 % of HBM "
+                     "bandwidth, in a tensor-bound kernel") if traffic else None)
     roofline = {"bound": "tensor", "achieved": ach_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": ach_tflops / peaks["tflops"], "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peaks["source"],
