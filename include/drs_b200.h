@@ -38,7 +38,10 @@ const char* drs_last_error(void);
  * exchange) are launched cooperatively, so the driver guarantees that the whole grid is resident or refuses; the
  * scan additionally asks cudaOccupancyMaxActiveClusters and runs WITHOUT the barrier when the grid cannot be
  * co-resident ("debug.coop_fallbacks" counts those launches).  Calls on one workspace must be issued from one
- * stream at a time. */
+ * stream at a time.
+ * "tune.k_split" (default 0 = auto; 1 = off; n > 1 = n slices): the loss gradients wrt q through a long K
+ * (dq = Hq x queue, dq = W x prototypes: one or two output tiles, K = queue length) are computed as K slices on
+ * many clusters and summed in slice order (deterministic).  Set it BEFORE the *_workspace_bytes query of the call. */
 int drs_set_option(const char* name, int value);
 /* Debug: {flag, tag, block, thread, parity, extra} of the last pipeline wait that timed out (a
  * kernel whose mbarrier wait exceeds a few seconds records this in mapped host memory and traps,

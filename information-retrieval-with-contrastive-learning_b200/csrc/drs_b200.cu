@@ -66,6 +66,7 @@ struct Options {
   int m_block = 0;         // search: A tiles per super-block of the unit order: 0 auto (= clusters), -1 off
   int df_tile = 0;         // InfoNCE dF = H F GEMM tile width: 0 auto, 256, 192
   int fp32_mode = 0;       // DRS_F32 search: 0 = 3 x TF32 on tcgen05 (when dim % 4 == 0 and 16-byte aligned), 1 = FFMA kernel
+  int k_split = 0;         // loss gradients wrt q through a long K (dq = Hq x queue, dq = W x prototypes): 0 auto, 1 off, > 1 that many K slices
   int cooperative = 1;     // launch the kernels that spin on grid-wide flags cooperatively (driver-checked co-residency)
   int coop_fallbacks = 0;  // read-only counter: launches that gave up the round barrier (grid not co-resident)
 } g_opt;
@@ -223,7 +224,31 @@ drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int 
   s.epi_tma_store = 0;
   s.a_sym = 0;
   s.skip_below_diagonal = 0;
+  s.k_splits = 1;
+  s.kb_per_split = dim_k_blocks;
   return s;
+}
+
+// Split-K for a GEMM whose output is a tile or two but whose K is long (the loss gradients wrt q through the MoCo queue
+// or the prototypes: [n x K] x [K x dim] with K = 12 544 at n = dim = 128): without it one cluster walks all of K (67 us
+// at the reference's shapes) while 73 idle.  `total_kb` = K blocks of the kernel that will run (64 wide on the
+// tensor-core path, 16 on the FFMA path); slices of >= `min_kb` blocks, at most 64 of them (the partial products are
+// [slices][rows_a][rows_b] fp32 in the workspace, summed in slice order by splitk_reduce_kernel).
+void plan_k_split(drs::GemmShape* s, int total_kb, int groups, int min_kb) {
+  s->k_splits = 1;
+  s->kb_per_split = total_kb;
+  const int base = s->num_m_tiles * s->num_splits;
+  int want = 1;
+  if (g_opt.k_split > 1) want = g_opt.k_split;
+  else if (g_opt.k_split == 0 && 2 * base <= groups && total_kb >= 4 * min_kb) want = std::min(groups / base, total_kb / min_kb);
+  want = std::max(1, std::min({want, 64, total_kb}));
+  if (want > 1) {
+    s->kb_per_split = (total_kb + want - 1) / want;
+    s->k_splits = (total_kb + s->kb_per_split - 1) / s->kb_per_split;   // no empty slice
+  }
+}
+inline size_t k_split_bytes(const drs::GemmShape& s) {
+  return s.k_splits > 1 ? static_cast<size_t>(s.k_splits) * s.rows_a * s.rows_b * sizeof(float) : 0;
 }
 
 constexpr int kTcColGroups = drs::GemmCfg<1>::EPI_GROUPS;
@@ -382,6 +407,8 @@ int launch_gemm_tc(const void* a, const void* b, int kdim, drs::GemmShape shp, i
     if (int rc = make_tmap_f32(&ta_lo, a_lo, rows_a_map, kdim, Cfg::BM)) return rc;
     if (int rc = make_tmap_f32(&tb_lo, b_lo, shp.rows_b, kdim, Cfg::BN_CTA)) return rc;
   }
+  if (shp.k_splits > 1 && (shp.a_sym || shp.skip_below_diagonal || shp.round_counter != nullptr))
+    return fail(DRS_ERR_INVALID, "internal: split-K is not combined with the symmetric schedules or the round barrier");
   auto kern = drs::gemm_nt_tc_kernel<CG, Epi, BN, PREC>;
   static thread_local bool attr_set[64] = {};
   static thread_local int max_clusters[64] = {};
@@ -585,6 +612,7 @@ int drs_set_option(const char* name, int value) {
   else if (!strcmp(name, "tune.round_barrier")) g_opt.round_barrier = value;
   else if (!strcmp(name, "tune.seed_thresholds")) g_opt.seed_thresholds = value;
   else if (!strcmp(name, "tune.symmetric_grad")) g_opt.symmetric_grad = value;
+  else if (!strcmp(name, "tune.k_split")) g_opt.k_split = value;
   else if (!strcmp(name, "tune.cooperative")) g_opt.cooperative = value;
   else if (!strcmp(name, "search.fp32_mode")) g_opt.fp32_mode = value;
   else if (!strcmp(name, "infonce.df_tile")) g_opt.df_tile = value;
@@ -607,6 +635,7 @@ int drs_get_option(const char* name, int* value) {
   else if (!strcmp(name, "tune.round_barrier")) *value = g_opt.round_barrier;
   else if (!strcmp(name, "tune.seed_thresholds")) *value = g_opt.seed_thresholds;
   else if (!strcmp(name, "tune.symmetric_grad")) *value = g_opt.symmetric_grad;
+  else if (!strcmp(name, "tune.k_split")) *value = g_opt.k_split;
   else if (!strcmp(name, "tune.cooperative")) *value = g_opt.cooperative;
   else if (!strcmp(name, "search.fp32_mode")) *value = g_opt.fp32_mode;
   else if (!strcmp(name, "infonce.df_tile")) *value = g_opt.df_tile;

@@ -35,17 +35,22 @@ gemm_simt_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, l
 
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
-  const int num_units = shp.num_m_tiles * shp.num_splits;
+  const int base_units = shp.num_m_tiles * shp.num_splits;
+  const int num_units = base_units * max(1, shp.k_splits);   // split-K: kb_per_split counts BK = 16 wide slices here
   const bool vec_ok = ((lda & 3) == 0) && ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
   Epi epi;
 
   for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-    const int m = u % shp.num_m_tiles, s = u / shp.num_m_tiles;
+    const int ks = shp.k_splits > 1 ? u / base_units : 0;
+    const int v = u - ks * base_units;
+    const int m = v % shp.num_m_tiles, s = v / shp.num_m_tiles;
     const int t0 = s * shp.tiles_per_split;
     const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
     const int row0 = m * C::BM;
-    if (tid < C::BM) epi.begin_unit(ep, row0 + tid, m, s);
+    const int k_lo = shp.k_splits > 1 ? ks * shp.kb_per_split * C::BK : 0;
+    const int k_hi = shp.k_splits > 1 ? min(K, k_lo + shp.kb_per_split * C::BK) : K;
+    if (tid < C::BM) epi.begin_unit(ep, row0 + tid, m, s + shp.num_splits * ks);
 
     for (int t = t0; t < t1; ++t) {
       const int col0 = t * C::BN;
@@ -136,13 +141,13 @@ gemm_simt_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, l
         }
       };
 
-      load_a(0);
-      load_b(0);
-      for (int k0 = 0; k0 < K; k0 += C::BK) {
+      load_a(k_lo);
+      load_b(k_lo);
+      for (int k0 = k_lo; k0 < k_hi; k0 += C::BK) {
         __syncthreads();  // previous slice fully consumed (and previous tile's scan finished)
         stage_to_smem();
         __syncthreads();
-        if (k0 + C::BK < K) {
+        if (k0 + C::BK < k_hi) {
           load_a(k0 + C::BK);
           load_b(k0 + C::BK);
         }

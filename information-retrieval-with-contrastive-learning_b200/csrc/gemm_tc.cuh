@@ -50,7 +50,23 @@ struct GemmShape {
   int skip_below_diagonal;      // A == B, square (A tile rows == B tile rows), symmetric output: only the tiles on and
                                 // above the diagonal are computed, dealt to the clusters as contiguous pieces of the
                                 // row-major triangle (TriangleWalk); the epilogue writes both halves
+  int k_splits;                 // > 1: split-K -- unit u covers K blocks [ks * kb_per_split, ...) of tile (u % base units) with
+  int kb_per_split;             // ks = u / base units, and the epilogue functor is handed split + num_splits * ks (a long-K
+                                // GEMM with one or two output tiles, e.g. dq = Hq x queue at N = 128, K = 12 544, would
+                                // otherwise run on one cluster: 67 us).  Not combined with a_sym / skip_below_diagonal.
 };
+
+// Unit u of a split-K launch -> (unit of the plain schedule, K-block range).
+__device__ __forceinline__ int unit_k_range(const GemmShape& shp, int u, int& kb0, int& kb1) {
+  kb0 = 0;
+  kb1 = shp.num_k_blocks;
+  if (shp.k_splits <= 1) return 0;
+  const int base = shp.num_m_tiles * shp.num_splits;
+  const int ks = u / base;
+  kb0 = ks * shp.kb_per_split;
+  kb1 = min(shp.num_k_blocks, kb0 + shp.kb_per_split);
+  return ks;
+}
 
 // Unit u -> (A tile m, split s).  Default order: u = s * num_m_tiles + m -- the clusters that run at the same time
 // share a B range.  With more A tiles than clusters (65 536 claims = 256 tiles on 74 clusters) that order walks ALL A
@@ -180,8 +196,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const bool leader = cta_rank == 0;
   const uint32_t cluster = (CG == 2) ? cluster_id_x() : blockIdx.x;
   const uint32_t nclusters = (CG == 2) ? num_clusters_x() : gridDim.x;
-  const int num_units = shp.num_m_tiles * shp.num_splits;
-  const int nkb = shp.num_k_blocks;
+  const int base_units = shp.num_m_tiles * shp.num_splits;
+  const int num_units = base_units * max(1, shp.k_splits);
 
   if (CG == 2) cluster_sync_all();  // both CTAs of the pair are resident before the paired TMEM alloc
 
@@ -223,10 +239,10 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const long long until = clock64() + static_cast<long long>(shp.stagger_cycles) * (cluster % shp.num_m_tiles);
         while (clock64() < until) {}
       }
-      auto load_tile = [&](int m, int t) {
+      auto load_tile = [&](int m, int t, int kb0, int kb1) {
         const int row_a = (m * CG + static_cast<int>(cta_rank)) * Cfg::BM;
         const int row_b = t * Cfg::BN + static_cast<int>(cta_rank) * Cfg::BN_CTA;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u, kTagProducerEmpty, stage);
           uint8_t* dst_a = smem_a + stage * Cfg::PARTS * Cfg::A_BYTES;
           uint8_t* dst_b = smem_b + stage * Cfg::PARTS * Cfg::B_BYTES;
@@ -267,7 +283,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       // it the groups drift apart by more than the L2 can hold and the corpus is re-read ~18x).
       // Every CTA of the grid is resident (checked and enforced by the launcher), so the spin cannot deadlock.
       if (shp.skip_below_diagonal) {
-        for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters); w.valid(); w.next()) load_tile(w.m, w.t);
+        for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters); w.valid(); w.next()) load_tile(w.m, w.t, 0, shp.num_k_blocks);
       } else {
         const int num_rounds = (num_units + static_cast<int>(nclusters) - 1) / static_cast<int>(nclusters);
         for (int round = 0; round < num_rounds; ++round) {
@@ -283,11 +299,12 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
           }
           if (u < num_units) {
-            int m, s;
-            unit_to_tile(shp, u, m, s);
+            int m, s, kb0, kb1;
+            unit_k_range(shp, u, kb0, kb1);
+            unit_to_tile(shp, u % base_units, m, s);
             const int t0 = s * shp.tiles_per_split;
             const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
-            for (int t = t0; t < t1; ++t) load_tile(m, t);
+            for (int t = t0; t < t1; ++t) load_tile(m, t, kb0, kb1);
           }
           if (shp.round_counter != nullptr) {
             if (elect_one_sync()) red_release_gpu_add_u32(shp.round_counter, 1u);
@@ -303,13 +320,14 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                              : (shp.f16_operands ? make_idesc_f16_f32(128 * CG, Cfg::BN) : make_idesc_bf16_f32(128 * CG, Cfg::BN));
       const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
       uint32_t stage = 0, phase = 0, it = 0;
-      auto mma_tile = [&](int m = 0) {
+      auto mma_tile = [&](int m, int kb0, int kb1) {
         const uint32_t acc = it % Cfg::ACC_STAGES, acc_phase = (it / Cfg::ACC_STAGES) & 1u;
         ++it;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, kTagMmaTmemEmpty, acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int kfirst = kb - kb0;     // 0 on the first K block of this unit: the accumulator is overwritten
           mbar_wait(&full_bar[stage], phase, kTagMmaFull, stage);
           tc_fence_after();
           const uint32_t a_addr = a_base + stage * (Cfg::PARTS * Cfg::A_BYTES);
@@ -323,12 +341,12 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 const uint64_t a_mn = make_sw128_mnmajor_desc(a_addr, 8192u, 1024u);
 #pragma unroll
                 for (int k = 0; k < Cfg::BK / Cfg::KSTEP; ++k)
-                  umma_bf16<CG>(d_tmem, a_mn + 128u * k, b_desc + 2u * k, idesc | kIdescAMajorMN, (kb | k) != 0 ? 1u : 0u);
+                  umma_bf16<CG>(d_tmem, a_mn + 128u * k, b_desc + 2u * k, idesc | kIdescAMajorMN, (kfirst | k) != 0 ? 1u : 0u);
               } else {
                 const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
 #pragma unroll
                 for (int k = 0; k < Cfg::BK / Cfg::KSTEP; ++k)   // +32 bytes (16 bf16) along K inside the 128-byte swizzle row
-                  umma_bf16<CG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                  umma_bf16<CG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kfirst | k) != 0 ? 1u : 0u);
               }
             } else {
               const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
@@ -336,27 +354,28 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               const uint32_t d_corr = d_tmem + Cfg::BN;                                                  // second accumulator
 #pragma unroll
               for (int k = 0; k < Cfg::BK / Cfg::KSTEP; ++k) {
-                umma_tf32<CG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);   // hi . hi
-                umma_tf32<CG>(d_corr, a_desc + 2u * k, b_lo + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);     // hi . lo
+                umma_tf32<CG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kfirst | k) != 0 ? 1u : 0u);   // hi . hi
+                umma_tf32<CG>(d_corr, a_desc + 2u * k, b_lo + 2u * k, idesc, (kfirst | k) != 0 ? 1u : 0u);     // hi . lo
                 umma_tf32<CG>(d_corr, a_lo + 2u * k, b_desc + 2u * k, idesc, 1u);                          // lo . hi
               }
             }
             umma_commit<CG>(&empty_bar[stage]);                       // smem slot free once these MMAs retire
-            if (kb == nkb - 1) umma_commit<CG>(&tmem_full_bar[acc]);  // accumulator complete
+            if (kb == kb1 - 1) umma_commit<CG>(&tmem_full_bar[acc]);  // accumulator complete
           }
           __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       };
       if (shp.skip_below_diagonal) {
-        for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters); w.valid(); w.next()) mma_tile();
+        for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters); w.valid(); w.next()) mma_tile(0, 0, shp.num_k_blocks);
       } else {
         for (int u = cluster; u < num_units; u += nclusters) {
-          int m, s;
-          unit_to_tile(shp, u, m, s);
+          int m, s, kb0, kb1;
+          unit_k_range(shp, u, kb0, kb1);
+          unit_to_tile(shp, u % base_units, m, s);
           const int t0 = s * shp.tiles_per_split;
           const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
-          for (int t = t0; t < t1; ++t) mma_tile(m);
+          for (int t = t0; t < t1; ++t) mma_tile(m, kb0, kb1);
         }
       }
     }
@@ -428,12 +447,13 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     } else {
       for (int u = cluster; u < num_units; u += nclusters) {
-        int m, s;
-        unit_to_tile(shp, u, m, s);
+        int m, s, kb0, kb1;
+        const int ks = unit_k_range(shp, u, kb0, kb1);
+        unit_to_tile(shp, u % base_units, m, s);
         const int t0 = s * shp.tiles_per_split;
         const int t1 = min(t0 + shp.tiles_per_split, shp.total_b_tiles);
         const int row = (m * CG + static_cast<int>(cta_rank)) * Cfg::BM + row_in_tile;
-        epi.begin_unit(ep, row, m, s);
+        epi.begin_unit(ep, row, m, s + shp.num_splits * ks);
         for (int t = t0; t < t1; ++t) epi_tile(row, t);
         epi.end_unit(ep, row, m, s * Cfg::EPI_GROUPS + group);
       }

@@ -416,22 +416,33 @@ struct StoreEpilogue {
     int rows_b;
     int split_row;
     int accumulate;  // 1: out += value
+    // split-K launches (GemmShape::k_splits > 1): K slice ks of the product goes, un-accumulated, to
+    // partials + ks * rows_a * rows_b as a compact [rows_a][rows_b] matrix; splitk_reduce_kernel sums the slices in a
+    // fixed order into out0 / out1 afterwards (deterministic, unlike atomic adds)
+    float* partials = nullptr;
+    int num_splits = 1;   // GemmShape::num_splits of the launch (begin_unit is handed split + num_splits * ks)
   };
   static constexpr bool kUsesScratch = false;
   static constexpr bool kStagesColumns = false;
-  __device__ __forceinline__ void begin_unit(const Params&, int, int, int) {}
+  float* slice = nullptr;
+  __device__ __forceinline__ void begin_unit(const Params& p, int, int, int split) {
+    if (p.partials != nullptr)
+      slice = p.partials + static_cast<long long>(split / p.num_splits) * p.rows_a * p.rows_b;
+  }
   __device__ __forceinline__ void chunk(const Params& p, int row, int col0, const uint32_t (&v)[32]) {
     if (row >= p.rows_a) return;
     const int valid = min(32, p.rows_b - col0);
     if (valid <= 0) return;
-    float* dst = (row < p.split_row ? p.out0 + static_cast<long long>(row) * p.ld_out
-                                    : p.out1 + static_cast<long long>(row - p.split_row) * p.ld_out) + col0;
+    const bool acc = p.accumulate && slice == nullptr;
+    float* dst = slice != nullptr ? slice + static_cast<long long>(row) * p.rows_b + col0
+                 : (row < p.split_row ? p.out0 + static_cast<long long>(row) * p.ld_out
+                                      : p.out1 + static_cast<long long>(row - p.split_row) * p.ld_out) + col0;
     if (valid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                __uint_as_float(v[j + 3]));
-        if (p.accumulate) {
+        if (acc) {
           const float4 old = *reinterpret_cast<const float4*>(dst + j);
           o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
         }
@@ -440,11 +451,25 @@ struct StoreEpilogue {
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j < valid) dst[j] = __uint_as_float(v[j]) + (p.accumulate ? dst[j] : 0.f);
+        if (j < valid) dst[j] = __uint_as_float(v[j]) + (acc ? dst[j] : 0.f);
     }
   }
   __device__ __forceinline__ void end_unit(const Params&, int, int, int) {}
 };
+
+// out (+)= sum over the K slices, slice 0 first (a fixed order: the result does not depend on which cluster ran which slice)
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partials, int k_splits, StoreEpilogue::Params p) {
+  const long long total = static_cast<long long>(p.rows_a) * p.rows_b;
+  for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += gridDim.x * 256ll) {
+    float acc = 0.f;
+    for (int ks = 0; ks < k_splits; ++ks) acc += partials[ks * total + e];
+    const int row = static_cast<int>(e / p.rows_b), col = static_cast<int>(e - static_cast<long long>(row) * p.rows_b);
+    float* dst = (row < p.split_row ? p.out0 + static_cast<long long>(row) * p.ld_out
+                                    : p.out1 + static_cast<long long>(row - p.split_row) * p.ld_out) + col;
+    *dst = p.accumulate ? *dst + acc : acc;
+  }
+}
 
 // ------------------------------------------------------------------------- helper kernels
 // Operand staging through 32 x 32 shared-memory tiles, so that the row-major copy AND the transposed

@@ -263,3 +263,29 @@ def test_loss_step_is_cuda_graph_capturable():
         l2 = crit(q2, k2, None)
         l2.backward()
         assert got[0] == l2.item() and torch.equal(got[1], q2.grad) and torch.equal(got[2], k2.grad)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_split_k_queue_gradient_at_the_reference_shapes(precision):
+    """The reference's own shapes (config.yaml: batch 128, 128-d, queue 12 544): dq through the queue is a
+    [128 x 12544] x [12544 x 128] product -- one output tile, long K -- computed as K slices on many clusters and
+    summed in slice order.  Same gradients as the unsplit product (tune.k_split = 1), bit-identical from run to run,
+    and both within the usual bars of the oracle."""
+    n, dim, klen = 128, 128, 12544
+    g = torch.Generator().manual_seed(7)
+    q = torch.nn.functional.normalize(torch.randn(n, dim, generator=g), dim=1)
+    k = torch.nn.functional.normalize(torch.randn(n, dim, generator=g) * 0.5 + q, dim=1)
+    queue = torch.nn.functional.normalize(torch.randn(dim, klen, generator=g), dim=0)
+    rl, rdq, rdk = infonce.nce_info_loss(q, k, queue, 0.05, dtype=torch.float64)
+    l1, dq1, dk1 = _run(q, k, queue, 0.05, precision)
+    l2, dq2, dk2 = _run(q, k, queue, 0.05, precision)
+    assert torch.equal(dq1, dq2) and torch.equal(dk1, dk2) and torch.equal(l1, l2)
+    drs_b200.set_option("tune.k_split", 1)
+    try:
+        l0, dq0, dk0 = _run(q, k, queue, 0.05, precision)
+    finally:
+        drs_b200.set_option("tune.k_split", 0)
+    assert torch.equal(l0, l1) and torch.equal(dk0, dk1)       # the split only touches dq
+    torch.testing.assert_close(dq1, dq0, rtol=1e-4, atol=1e-6 * float(dq0.abs().max()))
+    _assert_rows_close(dq1.numpy(), rdq.numpy(), precision)
+    _assert_rows_close(dk1.numpy(), rdk.numpy(), precision)

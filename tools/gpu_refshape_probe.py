@@ -62,5 +62,21 @@ def torch_step():
     (torch.nn.functional.cross_entropy(logits, tgt, reduction="sum") / 2).backward()
 
 
+crit32 = drs.NCELoss({"temperature": temp, "precision": "fp32"})
+
+
+def step32():
+    q.grad = None
+    k.grad = None
+    crit32(q, k, queue).backward()
+
+
+fp32_split = timed(step32)
+drs.set_option("tune.k_split", 1)
+fp32_plain = timed(step32, 10)
+bf16_plain = timed(step)
+drs.set_option("tune.k_split", 0)
+print(f"  precision='fp32' (FFMA kernels): eager {fp32_split * 1e3:.1f} us; without the split-K of dq = Hq x queue: fp32 {fp32_plain * 1e3:.1f} us, "
+      f"bf16 eager {bf16_plain * 1e3:.1f} us")
 print(f"NCELoss fwd+bwd at the reference shapes (N={n}, D={dim}, queue {klen}): eager {eager * 1e3:.1f} us, CUDA-graph replay {replay * 1e3:.1f} us, "
       f"torch closed form {timed(torch_step) * 1e3:.1f} us")
