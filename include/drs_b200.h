@@ -106,6 +106,23 @@ int drs_search_l2(const void* queries, int64_t nq, const void* corpus, int64_t n
                   void* stream);
 
 /*
+ * The other half of a k-means iteration and the distance statistics of the prototype "concentration" estimate.
+ * Replaces: the centroid update inside faiss.Clustering.train (src/contrastor/utils.py:28-36, :64 -- third-party,
+ * unpinned, absent: PARITY UNPINNED for the training) and the per-cluster distance lists of :73-83 (the reference's
+ * own numpy loops; pinned by tests/golden/kmeans_density.npz).
+ *
+ *   x        device [n, dim] fp32 samples (may be NULL when centroids is NULL)
+ *   order    device [n] int64: sample indices sorted by assigned cluster, STABLE (members in ascending sample order)
+ *   offsets  device [k + 1] int64: cluster c owns order[offsets[c] .. offsets[c + 1])
+ *   dist     device [n] fp32 squared distances to the assigned centroid (drs_search_l2 output), or NULL
+ *   centroids device [k, dim] fp32, in/out, or NULL: centroid c = mean of its members, summed in fp64 in member order
+ *            (deterministic; equal to a sequential float64 sum over the samples); an EMPTY cluster keeps its value
+ *   sum_sqrt_dist device [k] fp32 out (with dist): sum over the members of sqrt(dist)
+ */
+int drs_cluster_update(const float* x, int64_t n, int dim, const int64_t* order, const int64_t* offsets, int64_t k,
+                       const float* dist, float* centroids, float* sum_sqrt_dist, void* stream);
+
+/*
  * Sharded search with the exchange fused in: scan of this rank's shard, then ONE kernel that selects the
  * shard's top-k, stores it into every peer's gather buffer over NVLink peer memory, waits (per block of 32
  * claims, acquire/release flags at system scope) for the other shards' lists and merges them.  Replaces the

@@ -34,6 +34,7 @@ _SIGNATURES = {
     "drs_search_l2": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "drs_rerank": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     "drs_pair_scores": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
+    "drs_cluster_update": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "drs_doc_pairs_workspace_bytes": (c_int, [c_i64, c_i64, ctypes.POINTER(c_sz)]),
     "drs_doc_sentence_pairs": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp,
                                        c_sz, c_vp]),

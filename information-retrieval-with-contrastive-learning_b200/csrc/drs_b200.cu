@@ -16,6 +16,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "infonce.cuh"
+#include "kmeans.cuh"
 #include "merge.cuh"
 #include "pairs.cuh"
 #include "rerank.cuh"
@@ -869,5 +870,6 @@ int drs_merge_shards(const float* scores, const int64_t* ids, int num_shards, in
 #include "rerank_api.inc"
 #include "pairs_api.inc"
 #include "exchange_api.inc"
+#include "kmeans_api.inc"
 
 }  // extern "C"

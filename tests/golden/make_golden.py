@@ -22,6 +22,8 @@ What is executed, unmodified, from /root/reference:
   preprocessing/build_docs_sentence_similarity.py:52-65, restated verbatim in a local
   function because the module downloads nltk corpora at import time     -> pairs.npz
 * the commented dense diagnostic of src/evaluation.py:112, evaluated literally           -> paired.npz
+* ``src.contrastor.utils.run_kmeans`` over numpy stand-ins for the faiss objects (faiss is absent): the assignment
+  read-out and the concentration estimate of :67-101 are the reference's own code                -> kmeans_density.npz
 """
 import os
 import sys
@@ -187,8 +189,95 @@ def gen_paired():
                         per_pair=per_pair.numpy(), mean=np.float32(per_pair.mean().item()))
 
 
+def gen_kmeans():
+    """The reference's ``run_kmeans`` (src/contrastor/utils.py:50-105) ITSELF, executed over numpy stand-ins for the
+    faiss objects it builds (faiss is neither vendored nor installed): ``faiss.Clustering.train`` is the oracle's
+    Lloyd iteration, ``GpuIndexFlatL2.search`` an exact float64 squared-L2 argmin.  Everything after ``clus.train`` --
+    the assignment read-out, the per-cluster distance lists, the concentration estimate, its percentile clamp and
+    rescale, the centroid normalisation, the tensor conversions -- is the reference's own code, and that is what the
+    fixture pins.  The loader / model pair is a stand-in that hands out fixed embeddings (``extract_all_emb``, :11-25,
+    stacks anchor then positive embeddings per batch)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import kmeans as okm
+
+    class _Index:
+        def __init__(self, res, d, cfg):
+            self.d, self.mat = d, np.zeros((0, d), np.float32)
+
+        def add(self, x):
+            self.mat = np.vstack([self.mat, np.asarray(x, np.float32)])
+
+        def reset(self):
+            self.mat = np.zeros((0, self.d), np.float32)
+
+        def search(self, x, k):
+            assert k == 1
+            d, i = okm.assign(np.asarray(x, np.float32), self.mat)
+            return d[:, None], i[:, None]
+
+    class _Clustering:
+        def __init__(self, d, k):
+            self.d, self.k, self.centroids = d, k, None
+
+        def train(self, x, index):
+            c, _ = okm.lloyd(x, okm.init_centroids(x, self.k, self.seed), self.niter)
+            self.centroids = c.reshape(-1)
+            index.reset()
+            index.add(c)
+
+    fake = types.ModuleType("faiss")
+    fake.Clustering = _Clustering
+    fake.GpuIndexFlatL2 = _Index
+    fake.StandardGpuResources = lambda: None
+    fake.GpuIndexFlatConfig = lambda: types.SimpleNamespace(useFloat16=False, device=0)
+    fake.vector_to_array = lambda v: np.asarray(v)
+    sys.modules["faiss"] = fake
+    sys.modules["fastcluster"] = types.ModuleType("fastcluster")
+    sys.path.insert(0, REF)
+    cur = torch.cuda.current_device
+    torch.cuda.current_device = lambda: 0              # utils.py:59 asks for it; no GPU in the build container
+    try:
+        from src.contrastor import utils as ref_utils   # the reference
+    finally:
+        pass
+    g = torch.Generator().manual_seed(1337)
+    n_half, d = 300, 32
+    centers = _unit(torch.randn(12, d, generator=g))
+    lab = torch.randint(0, 12, (n_half,), generator=g)
+    anchor = _unit(centers[lab] + 0.15 * torch.randn(n_half, d, generator=g))
+    positive = _unit(centers[lab] + 0.15 * torch.randn(n_half, d, generator=g))
+    anchor[7] = anchor[3]                               # duplicates: zero distances and a cluster of identical points
+    batches = [(torch.arange(i, min(i + 64, n_half)), anchor[i:i + 64], positive[i:i + 64]) for i in range(0, n_half, 64)]
+
+    class _Model:
+        def bert_extract(self, a, p, device):
+            return a, p
+
+        def seq2vec(self, t):
+            return t
+
+    cfg = {"temperature": 0.05,
+           "cluster": {"num_cluster": [8, 16, 150], "verbose": False, "niter": 5, "nredo": 1,
+                       "max_points_per_centroid": 1000, "min_points_per_centroid": 1}}
+    try:
+        res = ref_utils.run_kmeans(cfg, batches, _Model(), "cpu")
+    finally:
+        torch.cuda.current_device = cur
+    x = ref_utils.extract_all_emb(batches, _Model(), "cpu")
+    out = {"x": x.astype(np.float32), "temperature": np.float32(cfg["temperature"]),
+           "num_cluster": np.asarray(cfg["cluster"]["num_cluster"]), "niter": np.int64(cfg["cluster"]["niter"])}
+    for s_, k in enumerate(cfg["cluster"]["num_cluster"]):
+        c, _ = okm.lloyd(x, okm.init_centroids(x, k, s_), cfg["cluster"]["niter"])   # what the stand-in trained (seed = position, :58)
+        out[f"raw_centroids_{s_}"] = c
+        out[f"centroids_{s_}"] = res["centroids"][s_].numpy()
+        out[f"density_{s_}"] = res["density"][s_].numpy()
+        out[f"emb2cluster_{s_}"] = res["emb2cluster"][s_].numpy()
+    np.savez_compressed(os.path.join(HERE, "kmeans_density.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(1337)
+    gen_kmeans()
     gen_infonce()
     gen_closest_docs()
     gen_pairs()
