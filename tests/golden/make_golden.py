@@ -24,6 +24,8 @@ What is executed, unmodified, from /root/reference:
 * the commented dense diagnostic of src/evaluation.py:112, evaluated literally           -> paired.npz
 * ``src.contrastor.utils.run_kmeans`` over numpy stand-ins for the faiss objects (faiss is absent): the assignment
   read-out and the concentration estimate of :67-101 are the reference's own code                -> kmeans_density.npz
+* ``RetrievalModelWrapper._dequeue_and_enqueue`` / ``_momentum_update_key_encoder``
+  (src/contrastor/contrastive_module.py:42-68), called unbound on a stand-in object           -> moco_queue.npz
 """
 import os
 import sys
@@ -275,8 +277,46 @@ def gen_kmeans():
     np.savez_compressed(os.path.join(HERE, "kmeans_density.npz"), **out)
 
 
+def gen_queue():
+    """``RetrievalModelWrapper._dequeue_and_enqueue`` and ``_momentum_update_key_encoder``
+    (src/contrastor/contrastive_module.py:42-68), the reference's own methods, called unbound on a stand-in object
+    (the constructor downloads BERT): a sequence of key batches, one of a size that does not divide the queue (the
+    reference then leaves the queue untouched, :59), wrapping around the end; two momentum steps on small encoders."""
+    sys.path.insert(0, REF)
+    from src.contrastor.contrastive_module import RetrievalModelWrapper as W   # the reference
+
+    g = torch.Generator().manual_seed(1337)
+    dim, size = 16, 48
+    me = types.SimpleNamespace(loss_config={"queue_size": size, "momentum": 0.9}, use_LSTM=False,
+                               queue=_unit(torch.randn(dim, size, generator=g), dim=0), queue_ptr=torch.zeros(1, dtype=torch.long))
+    out = {"queue0": me.queue.numpy().copy(), "momentum": np.float64(0.9)}
+    sizes = [12, 12, 7, 24, 12, 16]                     # 7 does not divide 48: skipped by the reference
+    for i, b in enumerate(sizes):
+        keys = _unit(torch.randn(b, dim, generator=g))
+        W._dequeue_and_enqueue(me, keys)
+        out[f"keys_{i}"] = keys.numpy()
+        out[f"queue_{i}"] = me.queue.numpy().copy()
+        out[f"ptr_{i}"] = np.int64(int(me.queue_ptr))
+    enc_q = torch.nn.Sequential(torch.nn.Linear(8, 5), torch.nn.Linear(5, 3))
+    enc_k = torch.nn.Sequential(torch.nn.Linear(8, 5), torch.nn.Linear(5, 3))
+    with torch.no_grad():
+        for p_ in list(enc_q.parameters()) + list(enc_k.parameters()):
+            p_.copy_(torch.randn(p_.shape, generator=g))
+    me.encoder_q, me.encoder_k = enc_q, enc_k
+    for j, p_ in enumerate(enc_q.parameters()):
+        out[f"pq_{j}"] = p_.detach().numpy().copy()
+    for j, p_ in enumerate(enc_k.parameters()):
+        out[f"pk_{j}"] = p_.detach().numpy().copy()
+    for step in range(2):
+        W._momentum_update_key_encoder(me)
+        for j, p_ in enumerate(enc_k.parameters()):
+            out[f"pk_{j}_after{step}"] = p_.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "moco_queue.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(1337)
+    gen_queue()
     gen_kmeans()
     gen_infonce()
     gen_closest_docs()

@@ -139,3 +139,32 @@ def test_default_vectoriser_is_the_references_and_says_so_when_nltk_is_missing()
     except ImportError:
         with pytest.raises(RuntimeError, match="vectorizer"):
             drs_b200.get_docs_sents_similarity([["a b"]], [["a b"]])
+
+
+def test_moco_queue_and_momentum_update_match_the_reference_methods():
+    """contrastive_module.py:42-68, against outputs of the reference's own methods (tests/golden/moco_queue.npz)."""
+    import os
+
+    import numpy as np
+    import torch
+
+    import drs_b200
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "moco_queue.npz"))
+    queue, ptr = torch.from_numpy(z["queue0"].copy()), torch.zeros(1, dtype=torch.long)
+    i = 0
+    while f"keys_{i}" in z.files:
+        drs_b200.dequeue_and_enqueue(queue, ptr, torch.from_numpy(z[f"keys_{i}"]))
+        np.testing.assert_array_equal(queue.numpy(), z[f"queue_{i}"])
+        assert int(ptr) == int(z[f"ptr_{i}"])
+        i += 1
+    assert i == 6
+    pq = [torch.nn.Parameter(torch.from_numpy(z[f"pq_{j}"].copy())) for j in range(4)]
+    pk = [torch.nn.Parameter(torch.from_numpy(z[f"pk_{j}"].copy()), requires_grad=False) for j in range(4)]
+    for step in range(2):
+        drs_b200.momentum_update(pq, pk, float(z["momentum"]))
+        for j in range(4):
+            np.testing.assert_array_equal(pk[j].detach().numpy(), z[f"pk_{j}_after{step}"])
+    q, p = drs_b200.new_queue(16, 48)
+    assert q.shape == (16, 48) and int(p) == 0
+    torch.testing.assert_close(q.norm(dim=0), torch.ones(48))
