@@ -3,7 +3,7 @@
 
 These are a strided copy and an axpy per parameter -- torch ops on whatever device the tensors live on, no engine
 kernel involved; they are here so that a wrapper built around ``drs_b200.NCELoss`` needs nothing else from the
-reference's module.  Pinned by tests/golden/moco_queue.npz (the reference's own methods, run by make_golden.py)."""
+reference's module.  Pinned by tests/golden/queue_maintenance.npz (the reference's own methods, run by make_golden.py)."""
 from __future__ import annotations
 
 import torch

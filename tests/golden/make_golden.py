@@ -25,7 +25,7 @@ What is executed, unmodified, from /root/reference:
 * ``src.contrastor.utils.run_kmeans`` over numpy stand-ins for the faiss objects (faiss is absent): the assignment
   read-out and the concentration estimate of :67-101 are the reference's own code                -> kmeans_density.npz
 * ``RetrievalModelWrapper._dequeue_and_enqueue`` / ``_momentum_update_key_encoder``
-  (src/contrastor/contrastive_module.py:42-68), called unbound on a stand-in object           -> moco_queue.npz
+  (src/contrastor/contrastive_module.py:42-68), called unbound on a stand-in object           -> queue_maintenance.npz
 """
 import os
 import sys
@@ -311,7 +311,7 @@ def gen_queue():
         W._momentum_update_key_encoder(me)
         for j, p_ in enumerate(enc_k.parameters()):
             out[f"pk_{j}_after{step}"] = p_.detach().numpy().copy()
-    np.savez_compressed(os.path.join(HERE, "moco_queue.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, "queue_maintenance.npz"), **out)
 
 
 if __name__ == "__main__":

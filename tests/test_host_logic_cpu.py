@@ -142,7 +142,7 @@ def test_default_vectoriser_is_the_references_and_says_so_when_nltk_is_missing()
 
 
 def test_moco_queue_and_momentum_update_match_the_reference_methods():
-    """contrastive_module.py:42-68, against outputs of the reference's own methods (tests/golden/moco_queue.npz)."""
+    """contrastive_module.py:42-68, against outputs of the reference's own methods (tests/golden/queue_maintenance.npz)."""
     import os
 
     import numpy as np
@@ -150,7 +150,7 @@ def test_moco_queue_and_momentum_update_match_the_reference_methods():
 
     import drs_b200
 
-    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "moco_queue.npz"))
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "queue_maintenance.npz"))
     queue, ptr = torch.from_numpy(z["queue0"].copy()), torch.zeros(1, dtype=torch.long)
     i = 0
     while f"keys_{i}" in z.files:
