@@ -71,6 +71,9 @@ def step32():
     crit32(q, k, queue).backward()
 
 
+if os.environ.get("REFSHAPE_BRIEF"):
+    print(f"NCELoss fwd+bwd at the reference shapes (N={n}, D={dim}, queue {klen}): eager {eager * 1e3:.1f} us, CUDA-graph replay {replay * 1e3:.1f} us")
+    sys.exit(0)
 fp32_split = timed(step32)
 drs.set_option("tune.k_split", 1)
 fp32_plain = timed(step32, 10)
