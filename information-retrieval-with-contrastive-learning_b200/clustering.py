@@ -39,6 +39,8 @@ def vector_to_array(v) -> np.ndarray:
 
 def _runs(assign: torch.Tensor, k: int):
     """Stable sort of the samples by cluster: (order int64 [n], offsets int64 [k + 1], counts int64 [k])."""
+    if assign.numel() and (int(assign.min()) < 0 or int(assign.max()) >= k):
+        raise ValueError(f"cluster ids must lie in [0, {k}), got [{int(assign.min())}, {int(assign.max())}]")
     order = torch.sort(assign, stable=True).indices
     counts = torch.bincount(assign, minlength=k)
     offsets = torch.zeros(k + 1, dtype=torch.int64, device=assign.device)
@@ -62,8 +64,14 @@ def update_centroids(x: torch.Tensor, assign: torch.Tensor, centroids: torch.Ten
     """One centroid update in place: mean of the members; an empty cluster is re-seeded next to the currently largest
     one, both moved apart by +-1/1024 per coordinate (faiss's ``split_clusters`` picks the donor at random in
     proportion to its size; taking the largest keeps the step deterministic).  Returns the number of splits."""
+    if not (x.is_cuda and assign.is_cuda and centroids.is_cuda):
+        raise RuntimeError("update_centroids needs CUDA tensors: there is no CPU path")
+    if x.dtype != torch.float32 or centroids.dtype != torch.float32 or not x.is_contiguous() or not centroids.is_contiguous():
+        raise ValueError("x and centroids must be contiguous float32 matrices")
+    if x.dim() != 2 or centroids.dim() != 2 or x.shape[1] != centroids.shape[1] or assign.shape != (x.shape[0],):
+        raise ValueError(f"shape mismatch: x {tuple(x.shape)}, assign {tuple(assign.shape)}, centroids {tuple(centroids.shape)}")
     k = centroids.shape[0]
-    order, offsets, counts = _runs(assign, k)
+    order, offsets, counts = _runs(assign.to(torch.int64).contiguous(), k)
     _cluster_update(x, order, offsets, k, centroids=centroids)
     empty = (counts == 0).nonzero().flatten()
     if empty.numel() == 0:

@@ -168,3 +168,13 @@ def test_moco_queue_and_momentum_update_match_the_reference_methods():
     q, p = drs_b200.new_queue(16, 48)
     assert q.shape == (16, 48) and int(p) == 0
     torch.testing.assert_close(q.norm(dim=0), torch.ones(48))
+
+
+def test_clustering_has_no_cpu_path():
+    import pytest
+    import torch
+
+    import drs_b200
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        drs_b200.update_centroids(torch.randn(10, 8), torch.zeros(10, dtype=torch.int64), torch.randn(3, 8))

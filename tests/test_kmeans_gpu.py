@@ -95,3 +95,14 @@ def test_fewer_points_than_clusters_is_an_error():
     clus = drs_b200.Clustering(16, 50)
     with pytest.raises(RuntimeError, match="at least as large as number of clusters"):
         clus.train(torch.randn(20, 16), drs_b200.FlatL2Index(16, device=DEV))
+
+
+def test_bad_arguments_are_reported():
+    x = torch.randn(10, 8, device=DEV)
+    cent = torch.randn(3, 8, device=DEV)
+    with pytest.raises(ValueError, match="cluster ids must lie"):
+        drs_b200.update_centroids(x, torch.full((10,), 3, device=DEV), cent)
+    with pytest.raises(ValueError, match="shape mismatch"):
+        drs_b200.update_centroids(x, torch.zeros(9, dtype=torch.int64, device=DEV), cent)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        drs_b200.update_centroids(x.cpu(), torch.zeros(10, dtype=torch.int64), cent.cpu())
