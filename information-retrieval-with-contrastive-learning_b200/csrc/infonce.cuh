@@ -137,7 +137,7 @@ struct GradLogitEpilogue {
     int n_rows_q;            // mode 1: N (second LSE is lse2[row + N])
     float scale_log2;
     float coef;
-    int debug = 0;           // tuning instrumentation (debug.flags): 8 skip the stores
+    int debug = 0;           // tuning instrumentation (debug.flags): 8 skip the stores, 16 never share one 2^y between the two softmax terms
     int mirror_rows = 0;     // mode 0, H symmetric: rows per A tile (256) when the tiles below the diagonal block are
                              // not computed (GemmShape::skip_below_diagonal): a chunk above it is also written transposed
   };
@@ -145,11 +145,25 @@ struct GradLogitEpilogue {
   static constexpr bool kStagesColumns = sizeof(OutT) == 2;   // mode 0 needs the LSE of every COLUMN: staged per tile by the kernel
   uint8_t* scratch = nullptr;  // per-warp smem staging (tensor-core kernel only), see store32_coalesced
   const CUtensorMap* out_map = nullptr;  // when set: chunks leave through TMA stores (store32_tma)
-  const float* cols = nullptr; // the 32 column LSEs of the current chunk in shared memory (tensor-core kernel only)
+  const float* cols = nullptr; // the 32 staged column values of the current chunk in shared memory (tensor-core kernel only)
   float li, li2, c;
+  // One MUFU per score instead of two.  Both softmax terms of a score share 2^y:
+  //   mode 0:  c (2^(y - L_i) + 2^(y - L_j)) = 2^(y - L_i) (c + u_i v_j),  u_i = c 2^(L_i - ref),  v_j = 2^(ref - L_j)
+  //   mode 1:  c (2^(y - L_i) + 2^(y - L_i')) = 2^(y - L_i) w_i,           w_i = c (1 + 2^(L_i - L_i'))
+  // (the epilogue of this GEMM is MUFU-bound: 2 x 32 768 ex2 per 128 x 256 tile at 16 per clock = 4096 clocks against the
+  //  3072 the tile's MMAs take.)  ref = the LSE of row 0 -- it cancels, it only centres the two factors.  The factors are
+  // used only while |L - ref| <= kFactorRange: u_i v_j then stays below 2^60, and a first term flushed to zero
+  // (y - L_i < -126) hides at most 2^-66 of the second one.  A warp whose rows, or a chunk whose columns, lie further
+  // out (temperatures far below the reference's 0.05 on unnormalised rows) takes the two-MUFU form.
+  static constexpr float kFactorRange = 30.f;
+  float ref = 0.f, ui = 0.f;
+  bool rows_centred = false;
 
+  // staged per tile column (mode 0): v_j, or -1 when column j is out of the factor range
   __device__ __forceinline__ float column_value(const Params& p, int col) const {
-    return (p.mode == 0 && col < p.rows_b) ? __ldg(p.lse2 + col) : 0.f;
+    if (p.mode != 0 || col >= p.rows_b) return 0.f;
+    const float d = ref - __ldg(p.lse2 + col);
+    return fabsf(d) <= kFactorRange ? fast_ex2(d) : -1.f;
   }
 
   __device__ __forceinline__ void begin_unit(const Params& p, int row, int, int) {
@@ -157,6 +171,18 @@ struct GradLogitEpilogue {
     li = p.lse2[r];
     li2 = (p.mode == 1) ? p.lse2[r + p.n_rows_q] : 0.f;
     c = p.coef * __ldg(p.grad);
+    if (p.mode == 0) {
+      if constexpr (kStagesColumns) {   // tensor-core kernel: whole warps call begin_unit, and the columns are staged
+        ref = __ldg(p.lse2);
+        const float d = li - ref;
+        ui = c * fast_ex2(fminf(fmaxf(d, -kFactorRange), kFactorRange));
+        rows_centred = __all_sync(0xffffffffu, fabsf(d) <= kFactorRange) && !(p.debug & 16);
+      }
+    } else if (p.mode == 1) {
+      const float d = li - li2;
+      rows_centred = fabsf(d) <= 2.f * kFactorRange && !(p.debug & 16);
+      ui = c + c * fast_ex2(fminf(fmaxf(d, -2.f * kFactorRange), 2.f * kFactorRange));   // w_i
+    }
   }
   static __device__ __forceinline__ void store32(OutT* dst, const float (&h)[32]) {
     if constexpr (sizeof(OutT) == 2) {
@@ -297,17 +323,32 @@ struct GradLogitEpilogue {
         if (!live && !staged) return;  // (a dead lane still takes part in the staged store of its warp)
         float h[32];
         if (p.mode == 0) {
-          // column LSEs: from the kernel's per-tile shared-memory stage when there is one (broadcast reads, no
-          // global-memory latency inside the chunk), else from global memory
-          const float4* lp = reinterpret_cast<const float4*>(cols != nullptr ? cols : p.lse2 + col0);  // 16-byte aligned
+          // the factors v_j of the chunk's columns come from the kernel's per-tile shared-memory stage (broadcast
+          // reads); without a stage (FFMA kernel), or out of the factor range, the column LSEs come from global memory
+          bool factored = false;
+          if (cols != nullptr)    // (staged: the whole warp is here)
+            factored = rows_centred && !__any_sync(0xffffffffu, cols[threadIdx.x & 31] < 0.f);
+          if (factored) {
+            const float4* vp = reinterpret_cast<const float4*>(cols);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 lj = cols != nullptr ? lp[j4] : __ldg(lp + j4);
-            const float ljs[4] = {lj.x, lj.y, lj.z, lj.w};
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 vj = vp[j4];
+              const float vjs[4] = {vj.x, vj.y, vj.z, vj.w};
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float s = __uint_as_float(v[4 * j4 + t]);
-              h[4 * j4 + t] = c * (fast_ex2(fmaf(s, p.scale_log2, -li)) + fast_ex2(fmaf(s, p.scale_log2, -ljs[t])));
+              for (int t = 0; t < 4; ++t)
+                h[4 * j4 + t] = fast_ex2(fmaf(__uint_as_float(v[4 * j4 + t]), p.scale_log2, -li)) * fmaf(ui, vjs[t], c);
+            }
+          } else {
+            const float4* lp = reinterpret_cast<const float4*>(p.lse2 + col0);  // 16-byte aligned
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 lj = __ldg(lp + j4);
+              const float ljs[4] = {lj.x, lj.y, lj.z, lj.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float s = __uint_as_float(v[4 * j4 + t]);
+                h[4 * j4 + t] = c * (fast_ex2(fmaf(s, p.scale_log2, -li)) + fast_ex2(fmaf(s, p.scale_log2, -ljs[t])));
+              }
             }
           }
           if (static_cast<unsigned>(diag) < 32u || static_cast<unsigned>(posj) < 32u) {
@@ -318,10 +359,15 @@ struct GradLogitEpilogue {
             }
           }
         } else if (p.mode == 1) {
+          if (rows_centred) {   // per thread: the two LSEs of this row are close enough to share one 2^y
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float s = __uint_as_float(v[j]);
-            h[j] = c * (fast_ex2(fmaf(s, p.scale_log2, -li)) + fast_ex2(fmaf(s, p.scale_log2, -li2)));
+            for (int j = 0; j < 32; ++j) h[j] = fast_ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -li)) * ui;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float s = __uint_as_float(v[j]);
+              h[j] = c * (fast_ex2(fmaf(s, p.scale_log2, -li)) + fast_ex2(fmaf(s, p.scale_log2, -li2)));
+            }
           }
         } else {
 #pragma unroll

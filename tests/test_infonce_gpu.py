@@ -207,7 +207,10 @@ def test_symmetric_gradient_matrix_matches_the_full_computation(n, dim):
     """Backward at whole 256-row tiles computes only the blocks of H = dL/dS on and above the diagonal.  Mode 2 (default)
     stores them once and the dF = H F GEMM reads the blocks below the diagonal TRANSPOSED out of the stored ones
     (MN-major tcgen05 operand); mode 1 writes every block twice (itself and its transpose); mode 0 computes all of H.
-    All three must give the same gradients (same bf16 H values, same accumulation order) and match the oracle."""
+    Modes 1 and 2 must give the same gradients (same bf16 H values, same accumulation order); mode 0 evaluates the
+    blocks below the diagonal from their own rows' side (2^(y - L_j) (c + u_j v_i) instead of the transpose of
+    2^(y - L_i) (c + u_i v_j), GradLogitEpilogue), so single bf16 values of H may round the other way: equal to a few
+    1e-4 of the gradient scale.  All match the oracle."""
     g = torch.Generator().manual_seed(5)
     q = torch.nn.functional.normalize(torch.randn(n, dim, generator=g), dim=1)
     k = torch.nn.functional.normalize(torch.randn(n, dim, generator=g) * 0.5 + q, dim=1)
@@ -223,12 +226,48 @@ def test_symmetric_gradient_matrix_matches_the_full_computation(n, dim):
     for mode in (1, 2):
         loss, dq, dk = res[mode]
         assert loss.item() == loss0.item()
-        assert (dq - dq0).abs().max().item() <= 1e-6 * scale and (dk - dk0).abs().max().item() <= 1e-6 * scale, mode
+        assert (dq - dq0).abs().max().item() <= 1e-3 * scale and (dk - dk0).abs().max().item() <= 1e-3 * scale, mode
+    assert (res[1][1] - res[2][1]).abs().max().item() <= 1e-6 * scale and (res[1][2] - res[2][2]).abs().max().item() <= 1e-6 * scale
     rl, rdq, rdk = infonce.nce_info_loss(q, k, None, 0.05, dtype=torch.float64)
     assert (res[2][1].double() - rdq).abs().max().item() <= 3e-2 * rdq.abs().max().item()
     assert (res[2][2].double() - rdk).abs().max().item() <= 3e-2 * rdk.abs().max().item()
     _assert_rows_close(res[2][1].numpy(), rdq.numpy(), "bf16")
     _assert_rows_close(res[2][2].numpy(), rdk.numpy(), "bf16")
+
+
+@pytest.mark.parametrize("temp,spread,klen", [(0.05, 0.0, 0), (0.05, 0.0, 256), (0.05, 0.6, 256), (0.01, 0.6, 256), (0.004, 0.8, 0)])
+def test_shared_exponential_form_and_its_fallback(temp, spread, klen):
+    """GradLogitEpilogue evaluates 2^(y - L_i) once per score and derives the second softmax term from it through
+    per-row / per-column factors while the LSEs lie within 2^30 of a reference row, and falls back to two exponentials per
+    score elsewhere.  Rows of very different norms and temperatures far below the reference's 0.05 put warps and
+    column chunks on both sides of that bound: the result must equal the two-exponential form (debug.flags = 16, the
+    formulation the goldens pinned) to bf16 rounding of single H values, and match the oracle fed the same
+    bf16-rounded embeddings."""
+    n, dim = 512, 128
+    g = torch.Generator().manual_seed(23)
+    scale_rows = 1.0 + spread * (2.0 * torch.rand(n, 1, generator=g) - 1.0)
+    q = torch.nn.functional.normalize(torch.randn(n, dim, generator=g), dim=1) * scale_rows
+    k = torch.nn.functional.normalize(torch.randn(n, dim, generator=g) * 0.5 + q, dim=1) * scale_rows.flip(0)
+    queue = torch.nn.functional.normalize(torch.randn(dim, klen, generator=g), dim=0) if klen else None
+    q, k = q.bfloat16().float(), k.bfloat16().float()
+    queue = queue.bfloat16().float() if klen else None
+    try:
+        drs_b200.set_option("debug.flags", 16)
+        loss_two, dq_two, dk_two = _run(q, k, queue, temp, "bf16")
+    finally:
+        drs_b200.set_option("debug.flags", 0)
+    loss, dq, dk = _run(q, k, queue, temp, "bf16")
+    assert loss.item() == loss_two.item()
+    scale = max(dq_two.abs().max().item(), dk_two.abs().max().item())
+    assert torch.isfinite(dq).all() and torch.isfinite(dk).all()
+    assert (dq - dq_two).abs().max().item() <= 2e-3 * scale and (dk - dk_two).abs().max().item() <= 2e-3 * scale
+    rl, rdq, rdk = infonce.nce_info_loss(q, k, queue, temp, dtype=torch.float64)
+    assert abs(loss.item() - rl.item()) <= 1e-3 * abs(rl.item())
+    rscale = max(rdq.abs().max().item(), rdk.abs().max().item())
+    assert (dq.double() - rdq).abs().max().item() <= 3e-2 * rscale and (dk.double() - rdk).abs().max().item() <= 3e-2 * rscale
+    if temp >= 0.01:   # (at T = 0.004 single rows of the bf16 path -- either form -- are off by tens of per cent: H in bf16)
+        _assert_rows_close(dq.numpy(), rdq.numpy(), "bf16")
+        _assert_rows_close(dk.numpy(), rdk.numpy(), "bf16")
 
 
 def test_loss_step_is_cuda_graph_capturable():
