@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <numeric>
+#include <type_traits>
 
 #include "../../include/drs_b200.h"
 #include "epilogues.cuh"
@@ -62,6 +63,7 @@ struct Options {
   int round_barrier = 1;
   int seed_thresholds = 1;
   int symmetric_grad = 2;   // InfoNCE backward: 0 full H, 1 upper tiles computed + mirrored stores, 2 upper tiles only (dF reads transposed)
+  int symmetric_lse = 1;    // InfoNCE forward: only the tiles of S = F F^T on and above the diagonal (whole 256-row tiles, bounded logits)
   int tma_store = 1;       // InfoNCE backward: the gradient-of-logits tiles leave through TMA stores
   int fp32_tile = 128;     // B-tile width of the fp32 tensor-core scan: 128 (two accumulator stages: 0.66 ms on config 0) or 256 (one: 0.73 ms)
   int m_block = 0;         // search: A tiles per super-block of the unit order: 0 auto (= clusters), -1 off
@@ -220,6 +222,8 @@ drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int 
   s.stagger_cycles = g_opt.stagger_cycles;
   s.round_counter = nullptr;
   s.active = nullptr;
+  s.active_mode = 0;
+  s.active_scale = 0.f;
   s.f16_operands = 0;
   s.m_block = 0;
   s.epi_tma_store = 0;
@@ -378,6 +382,9 @@ int plan_search(int64_t nq, int64_t nc, int dim, int k, int dtype, SearchPlan* p
 // scan runs without the barrier (correct, more DRAM traffic) and `debug.coop_fallbacks` counts it.
 // PREC = 1 (fp32 operands as hi + lo, three kind::tf32 MMAs per K step): a / b are the hi parts -- any fp32 matrix,
 // the tensor core reads the top 19 bits of every word -- and a_lo / b_lo the matching residuals (split_f32_kernel).
+template <class Epi, class = void> struct epi_has_tma_output : std::false_type {};
+template <class Epi> struct epi_has_tma_output<Epi, std::enable_if_t<Epi::kTmaOutput>> : std::true_type {};
+
 template <int CG, class Epi, int BN = 256, int PREC = 0>
 int launch_gemm_tc(const void* a, const void* b, int kdim, drs::GemmShape shp, int grid,
                    const typename Epi::Params& ep, cudaStream_t st, int64_t a_rows_alloc = 0, int64_t pitch_a = 0,
@@ -391,7 +398,7 @@ int launch_gemm_tc(const void* a, const void* b, int kdim, drs::GemmShape shp, i
     ta_lo = ta;
     tb_lo = tb;
     if (shp.epi_tma_store) {   // the epilogue's output matrix (GradLogitEpilogue: ep.out, rows_a x rows_b, pitch ld_out)
-      if constexpr (Epi::kUsesScratch) {
+      if constexpr (epi_has_tma_output<Epi>::value) {
         if (int rc = make_tmap_out_bf16(&tb_lo, ep.out, ep.rows_a, ep.rows_b, ep.ld_out)) return rc;
       } else {
         return fail(DRS_ERR_INVALID, "internal: epi_tma_store needs an epilogue with an output matrix");
@@ -613,6 +620,7 @@ int drs_set_option(const char* name, int value) {
   else if (!strcmp(name, "tune.round_barrier")) g_opt.round_barrier = value;
   else if (!strcmp(name, "tune.seed_thresholds")) g_opt.seed_thresholds = value;
   else if (!strcmp(name, "tune.symmetric_grad")) g_opt.symmetric_grad = value;
+  else if (!strcmp(name, "tune.symmetric_lse")) g_opt.symmetric_lse = value;
   else if (!strcmp(name, "tune.k_split")) g_opt.k_split = value;
   else if (!strcmp(name, "tune.cooperative")) g_opt.cooperative = value;
   else if (!strcmp(name, "search.fp32_mode")) g_opt.fp32_mode = value;
@@ -636,6 +644,7 @@ int drs_get_option(const char* name, int* value) {
   else if (!strcmp(name, "tune.round_barrier")) *value = g_opt.round_barrier;
   else if (!strcmp(name, "tune.seed_thresholds")) *value = g_opt.seed_thresholds;
   else if (!strcmp(name, "tune.symmetric_grad")) *value = g_opt.symmetric_grad;
+  else if (!strcmp(name, "tune.symmetric_lse")) *value = g_opt.symmetric_lse;
   else if (!strcmp(name, "tune.k_split")) *value = g_opt.k_split;
   else if (!strcmp(name, "tune.cooperative")) *value = g_opt.cooperative;
   else if (!strcmp(name, "search.fp32_mode")) *value = g_opt.fp32_mode;

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256)
 gemm_simt_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, long long lda, long long ldb, int K,
                      const GemmShape shp, const typename Epi::Params ep) {
   using C = SimtCfg;
-  if (shp.active != nullptr && *shp.active == 0u) return;
+  if (!launch_gate_open(shp)) return;
   extern __shared__ float smem_f[];
   float* As = smem_f;                    // [BK][LDS]
   float* Bs = smem_f + C::BK * C::LDS;   // [BK][LDS]

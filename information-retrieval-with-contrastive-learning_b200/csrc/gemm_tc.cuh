@@ -37,7 +37,11 @@ struct GemmShape {
   int b_hint;           // L2 eviction hint for the B (corpus) tiles: 0 normal, 1 evict-first, 2 evict-last
   int stagger_cycles;   // producer start delay per A-tile index (experiment knob)
   unsigned int* round_counter;  // zeroed device counter for the per-round producer barrier, or nullptr
-  const unsigned int* active;   // optional: the whole launch is a no-op when *active == 0 (adaptive k > 32 passes)
+  const unsigned int* active;   // optional gate read on the device (launch_gate_open): the whole launch is a no-op when it is closed
+  int active_mode;              // 0: open while *active != 0 (adaptive k > 32 passes).  1: always open; *active holds the bits of
+  float active_scale;           // max_i |f_i|^2 (row_bound_kernel) and `skip_below_diagonal` applies only while the logits' span
+                                // 2 M, M = bounded_reference(active_scale, *active), is <= kBoundedSpan (the symmetric InfoNCE
+                                // forward; otherwise the launch walks the full matrix and its functor keeps running maxima)
   int f16_operands;             // 0: bf16 operands, 1: IEEE half operands (same kind::f16 MMA, other instruction descriptor)
   int epi_tma_store;            // the epilogue functor stores its tiles with TMA (cp.async.bulk.tensor) through `tmap_b_lo`,
                                 // which then describes the OUTPUT matrix (box 32 x 32, 64-byte swizzle); PREC == 0 only
@@ -55,6 +59,24 @@ struct GemmShape {
                                 // GEMM with one or two output tiles, e.g. dq = Hq x queue at N = 128, K = 12 544, would
                                 // otherwise run on one cluster: 67 us).  Not combined with a_sym / skip_below_diagonal.
 };
+
+// Common reference of the symmetric InfoNCE forward (infonce.cuh, SymLseEpilogue): M = scale * max_i |f_i|^2 (1 + 2^-10)
+// bounds every logit from above; with 2 M <= kBoundedSpan no term 2^(y - M) is flushed to zero.
+static constexpr float kBoundedSpan = 100.f;
+__device__ __forceinline__ float bounded_reference(float scale_log2, unsigned int max_norm2_bits) {
+  return scale_log2 * __uint_as_float(max_norm2_bits) * (1.f + 0x1p-10f);
+}
+__device__ __forceinline__ bool logits_bounded(float scale_log2, unsigned int max_norm2_bits) {
+  return 2.f * bounded_reference(scale_log2, max_norm2_bits) <= kBoundedSpan;   // false for inf / NaN
+}
+__device__ __forceinline__ bool launch_gate_open(const GemmShape& shp) {
+  return shp.active == nullptr || shp.active_mode != 0 || *shp.active != 0u;
+}
+// the symmetric schedule, unless the launch is gated on bounded logits and they are not
+__device__ __forceinline__ bool triangle_schedule(const GemmShape& shp) {
+  if (!shp.skip_below_diagonal) return false;
+  return shp.active == nullptr || shp.active_mode != 1 || logits_bounded(shp.active_scale, *shp.active);
+}
 
 // Unit u of a split-K launch -> (unit of the plain schedule, K-block range).
 __device__ __forceinline__ int unit_k_range(const GemmShape& shp, int u, int& kb0, int& kb1) {
@@ -170,7 +192,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                   const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_b_lo,
                   const GemmShape shp, const typename Epi::Params ep) {
   using Cfg = GemmCfg<CG, BN, PREC>;
-  if (shp.active != nullptr && *shp.active == 0u) return;  // uniform over the grid: nothing left to rescan
+  if (!launch_gate_open(shp)) return;  // uniform over the grid: nothing left to rescan
+  const bool triangle = triangle_schedule(shp);   // (uniform too)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                   // [stage][part] A tiles, then [stage][part] B tiles
@@ -282,7 +305,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       // and each B tile is fetched from HBM once per round instead of once per straggler (without
       // it the groups drift apart by more than the L2 can hold and the corpus is re-read ~18x).
       // Every CTA of the grid is resident (checked and enforced by the launcher), so the spin cannot deadlock.
-      if (shp.skip_below_diagonal) {
+      if (triangle) {
         for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters); w.valid(); w.next()) load_tile(w.m, w.t, 0, shp.num_k_blocks);
       } else {
         const int num_rounds = (num_units + static_cast<int>(nclusters) - 1) / static_cast<int>(nclusters);
@@ -366,7 +389,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       };
-      if (shp.skip_below_diagonal) {
+      if (triangle) {
         for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters); w.valid(); w.next()) mma_tile(0, 0, shp.num_k_blocks);
       } else {
         for (int u = cluster; u < num_units; u += nclusters) {
@@ -437,7 +460,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (!(shp.debug_flags & 1)) epi.chunk(ep, row, t * Cfg::BN + (group * Cfg::CHUNKS_PER_GROUP + c) * 32, v);
       }
     };
-    if (shp.skip_below_diagonal) {
+    if (triangle) {
       // every tile is its own unit (the functors used with this schedule keep no state across tiles)
       for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters); w.valid(); w.next()) {
         const int row = (w.m * CG + static_cast<int>(cta_rank)) * Cfg::BM + row_in_tile;

@@ -115,6 +115,149 @@ struct LseEpilogue {
   }
 };
 
+// ------------------------------------------------------------------------- forward, symmetric schedule
+// S = F F^T is symmetric: with whole 256-row tiles only the tiles on and above the diagonal are computed
+// (GemmShape::skip_below_diagonal, 528 of 1024 at 2N = 8192) and a tile above the diagonal serves BOTH its rows (sums
+// along the rows, as in LseEpilogue) and, transposed, the rows of its mirror image (sums down the columns).  A column
+// sum adds up values held by different threads, so all terms need ONE reference instead of per-row running maxima:
+//   M = scale * max_i |f_i|^2 * (1 + 2^-10) >= every y_ij (Cauchy-Schwarz),   term = 2^(y_ij - M) <= 1.
+// Nothing overflows; nothing is flushed to zero as long as y_ij - M >= -2M >= -kBoundedSpan, which the launch checks
+// on the device against the row bound (normalised rows: M = 28.9 at the reference's T = 0.05).  When the check fails
+// the same launch walks the full matrix instead (GemmShape::active_mode 1) and this functor hands every call to an
+// LseEpilogue (running maxima).
+//
+// Control words in the workspace (zeroed by the pack kernel): the loss-reduction counter and the row bound.
+enum : int { kCtlLossCounter = 0, kCtlBoundBits = 1 };
+
+// max_i |f_i|^2 over the bf16 operand rows (what the tensor core multiplies), a warp per row, one fire-and-forget
+// atomic max per block (non-negative floats order like their bit patterns).  The launches that follow derive M and
+// the choice of schedule from the word themselves (gemm_tc.cuh: bounded_reference, launch_gate_open).  dim % 8 == 0.
+__global__ void __launch_bounds__(256)
+row_bound_kernel(const __nv_bfloat16* __restrict__ f, int rows, int dim, unsigned int* __restrict__ ctl) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  float acc0 = 0.f, acc1 = 0.f;
+  if (row < rows) {
+    const uint4* src = reinterpret_cast<const uint4*>(f + static_cast<size_t>(row) * dim);
+    const int n16 = dim / 8;
+#pragma unroll 4
+    for (int i = lane; i < n16; i += 32) {
+      const uint4 w = __ldg(src + i);
+      const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float lo = __uint_as_float(ws[t] << 16), hi = __uint_as_float(ws[t] & 0xffff0000u);
+        acc0 = fmaf(lo, lo, acc0);
+        acc1 = fmaf(hi, hi, acc1);
+      }
+    }
+  }
+  float acc = acc0 + acc1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float warp_max[8];
+  if (lane == 0) warp_max[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mx = 0.f;
+    for (int w = 0; w < 8; ++w) mx = fmaxf(mx, warp_max[w]);   // (a NaN row drops out here; its NaN logits still reach the loss)
+    atomicMax(ctl + kCtlBoundBits, __float_as_uint(mx));
+  }
+}
+
+struct SymLseEpilogue {
+  struct Params {
+    float* rowpart;            // [rows][row_slots]  sum_j 2^(y_ij - M) over the columns of slot (tile t, column group)
+    float* colpart;            // [tiles * 8][col_pitch]  entry (m * 8 + w, j): sum_i 2^(y_ij - M) over the 32 rows of warp w of A tile m
+    int col_pitch;             // rows + 32: consecutive slots of a column are NOT a power of two apart (L2 slice camping)
+    float* pos;                // [rows] positive logit in natural units
+    const unsigned int* ctl;   // control words (M)
+    int rows;                  // 2N, a multiple of the 256-row tile
+    int row_slots;
+    int half;
+    float scale_log2;
+    float inv_t;
+    LseEpilogue::Params full;  // the stand-in when the logits are not bounded: (max, sum) partials of the full matrix
+  };
+  static constexpr bool kUsesScratch = false;
+  static constexpr bool kStagesColumns = false;
+  float l, mref;
+  int tile_m, tile_t;
+  bool bounded;
+  LseEpilogue full;
+
+  __device__ __forceinline__ void begin_unit(const Params& p, int row, int m, int t) {
+    const unsigned int bits = __ldg(p.ctl + kCtlBoundBits);
+    bounded = logits_bounded(p.scale_log2, bits);
+    if (!bounded) {
+      full.begin_unit(p.full, row, m, t);
+      return;
+    }
+    l = 0.f;
+    tile_m = m;
+    tile_t = t;
+    mref = bounded_reference(p.scale_log2, bits);
+  }
+  __device__ __forceinline__ void chunk(const Params& p, int row, int col0, const uint32_t (&v)[32]) {
+    if (!bounded) {
+      full.chunk(p.full, row, col0, v);
+      return;
+    }
+    const int lane = threadIdx.x & 31;
+    float e[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) e[j] = fast_ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mref));
+    const int pc = row < p.half ? row + p.half : row - p.half;
+    const int posj = pc - col0, diag = row - col0;
+    if (static_cast<unsigned>(posj) < 32u) {   // the positive of this row: also that of row pc, whose own walk never sees column `row`
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j == posj) {
+          const float s = __uint_as_float(v[j]) * p.inv_t;
+          p.pos[row] = s;
+          if (tile_t != tile_m) p.pos[pc] = s;
+        }
+    }
+    if (tile_t == tile_m && static_cast<unsigned>(diag) < 32u) {   // the diagonal is not a logit (contrastive_loss.py:65-68)
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j == diag) e[j] = 0.f;
+    }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      a0 += e[j + 0];
+      a1 += e[j + 1];
+      a2 += e[j + 2];
+      a3 += e[j + 3];
+    }
+    l += (a0 + a1) + (a2 + a3);
+    if (tile_t == tile_m) return;   // a diagonal tile holds both triangles of its block: its rows have seen every column
+    // Column sums over the warp's 32 rows: a transposing butterfly.  At distance d a lane keeps the half of its values
+    // whose column bit matches its own lane bit, hands the other half to its partner and adds what it receives: 16 + 8 +
+    // 4 + 2 + 1 shuffles, after which lane j holds the sum of column col0 + j.
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      const bool upper = (lane & d) != 0;
+#pragma unroll
+      for (int j = 0; j < d; ++j) {
+        const float send = upper ? e[j] : e[j + d];
+        const float keep = upper ? e[j + d] : e[j];
+        e[j] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+      }
+    }
+    const int warp_in_tile = ((row - lane) - tile_m * 256) >> 5;   // 0..7 over the CTA pair's 256 rows
+    p.colpart[static_cast<size_t>(tile_m * 8 + warp_in_tile) * p.col_pitch + col0 + lane] = e[0];
+  }
+  __device__ __forceinline__ void end_unit(const Params& p, int row, int m, int slot) {
+    if (!bounded) {
+      full.end_unit(p.full, row, m, slot);
+      return;
+    }
+    p.rowpart[static_cast<size_t>(row) * p.row_slots + slot] = l;
+  }
+};
+
 // ------------------------------------------------------------------------- backward: dL/dlogits
 //   mode 0 (in-batch, symmetrised so that dF = H F, contrastive_loss.py:62 has F on both sides):
 //          H[i][j] = c (2^(y_ij - L_i) + 2^(y_ij - L_j) - 2 [j == pos(i)]),  H[i][i] = 0
@@ -142,6 +285,7 @@ struct GradLogitEpilogue {
                              // not computed (GemmShape::skip_below_diagonal): a chunk above it is also written transposed
   };
   static constexpr bool kUsesScratch = sizeof(OutT) == 2;
+  static constexpr bool kTmaOutput = sizeof(OutT) == 2;      // `out` can be described by a tensor map (GemmShape::epi_tma_store)
   static constexpr bool kStagesColumns = sizeof(OutT) == 2;   // mode 0 needs the LSE of every COLUMN: staged per tile by the kernel
   uint8_t* scratch = nullptr;  // per-warp smem staging (tensor-core kernel only), see store32_coalesced
   const CUtensorMap* out_map = nullptr;  // when set: chunks leave through TMA stores (store32_tma)
@@ -475,19 +619,71 @@ struct StoreEpilogue {
     // fixed order into out0 / out1 afterwards (deterministic, unlike atomic adds)
     float* partials = nullptr;
     int num_splits = 1;   // GemmShape::num_splits of the launch (begin_unit is handed split + num_splits * ks)
+    int debug = 0;        // tuning instrumentation (debug.flags): 32 store every row directly (no staging)
   };
-  static constexpr bool kUsesScratch = false;
+  static constexpr bool kUsesScratch = true;    // tensor-core kernel: a staging strip per warp (store_staged)
   static constexpr bool kStagesColumns = false;
+  uint8_t* scratch = nullptr;
+  const CUtensorMap* out_map = nullptr;   // (unused: set by the kernel for every functor with a scratch strip)
   float* slice = nullptr;
+  __device__ __forceinline__ void finish() const {}
   __device__ __forceinline__ void begin_unit(const Params& p, int, int, int split) {
     if (p.partials != nullptr)
       slice = p.partials + static_cast<long long>(split / p.num_splits) * p.rows_a * p.rows_b;
   }
+  __device__ __forceinline__ float* row_ptr(const Params& p, int row) const {
+    return slice != nullptr ? slice + static_cast<long long>(row) * p.rows_b
+                            : (row < p.split_row ? p.out0 + static_cast<long long>(row) * p.ld_out
+                                                 : p.out1 + static_cast<long long>(row - p.split_row) * p.ld_out);
+  }
+  // A thread owns a row, so a direct store instruction writes 16 bytes into each of 32 rows (32 half-filled sectors).
+  // Staged through the warp's shared-memory strip in two halves of 16 columns (32 rows x 64 bytes, pitch 80: the
+  // geometry of GradLogitEpilogue::store32_coalesced), four lanes cover a row's 64 bytes and one instruction writes 8
+  // rows x 2 whole sectors.  The whole warp calls; rows past the end are skipped on the way out.
+  __device__ __forceinline__ void store_staged(const Params& p, int row, int col0, const uint32_t (&v)[32], bool acc) const {
+    const int lane = threadIdx.x & 31;
+    constexpr int kPitch = 80;
+    const uint32_t base = smem_u32(scratch);
+    const uint32_t mine = base + lane * kPitch;
+    const int row0 = row - lane, piece = lane & 3;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(mine + 4 * j), "r"(v[16 * half + j]), "r"(v[16 * half + j + 1]),
+                     "r"(v[16 * half + j + 2]), "r"(v[16 * half + j + 3]) : "memory");
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (lane >> 2) + 8 * i;
+        float4 val;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(base + r * kPitch + 16 * piece) : "memory");
+        if (row0 + r < p.rows_a) {
+          float4* dst = reinterpret_cast<float4*>(row_ptr(p, row0 + r) + col0 + 16 * half + 4 * piece);
+          if (acc) {
+            const float4 old = *dst;
+            val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+          }
+          *dst = val;
+        }
+      }
+      __syncwarp();   // the strip is reused by the next half / chunk
+    }
+  }
   __device__ __forceinline__ void chunk(const Params& p, int row, int col0, const uint32_t (&v)[32]) {
-    if (row >= p.rows_a) return;
     const int valid = min(32, p.rows_b - col0);
     if (valid <= 0) return;
     const bool acc = p.accumulate && slice == nullptr;
+    if (scratch != nullptr && valid == 32 && !(p.debug & 32)) {   // (uniform over the warp)
+      const long long pitch = slice != nullptr ? p.rows_b : p.ld_out;
+      const uintptr_t bases = slice != nullptr ? reinterpret_cast<uintptr_t>(slice)
+                                               : (reinterpret_cast<uintptr_t>(p.out0) | reinterpret_cast<uintptr_t>(p.out1));
+      if ((pitch & 3) == 0 && (bases & 15) == 0) {
+        store_staged(p, row, col0, v, acc);
+        return;
+      }
+    }
+    if (row >= p.rows_a) return;
     float* dst = slice != nullptr ? slice + static_cast<long long>(row) * p.rows_b + col0
                  : (row < p.split_row ? p.out0 + static_cast<long long>(row) * p.ld_out
                                       : p.out1 + static_cast<long long>(row - p.split_row) * p.ld_out) + col0;
@@ -571,12 +767,12 @@ pack_transpose_kernel(const float* __restrict__ s0, const float* __restrict__ s1
 
 // The InfoNCE operands: F = cat(q, k) [R = 2N][C] fp32 -> bf16 F (row-major) and bf16 F^T [C][R], 64 x 64 tiles, every
 // global access a full 128-byte line (float4 loads, 8-byte / 16-byte bf16 stores).  C % 4 == 0, R % 8 == 0 (the bf16
-// path requires dim % 8 and n % 4).  Also zeroes the word the fused loss reduction counts finished blocks in.
+// path requires dim % 8 and n % 4).  Also zeroes the control words the fused loss reduction and row_bound_kernel count in.
 __global__ void __launch_bounds__(256)
 pack_cat_bf16_kernel(const float* __restrict__ s0, const float* __restrict__ s1, int split, int R, int C,
                      __nv_bfloat16* __restrict__ obf, __nv_bfloat16* __restrict__ obf_t, unsigned int* __restrict__ zero_word) {
   __shared__ float tile[64][65];
-  if (blockIdx.x == 0 && threadIdx.x == 0 && zero_word != nullptr) *zero_word = 0u;
+  if (blockIdx.x == 0 && threadIdx.x < 2 && zero_word != nullptr) zero_word[threadIdx.x] = 0u;   // loss counter, row bound (kCtl...)
   const int tiles_c = (C + 63) / 64, tiles_r = (R + 63) / 64;
   const int tid = threadIdx.x;
   for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
@@ -623,6 +819,34 @@ __device__ __forceinline__ void lse_combine(float& m, float& l, float m2, float 
   if (mn == -INFINITY) return;  // both empty
   l = l * exp2f(m - mn) + l2 * exp2f(m2 - mn);
   m = mn;
+}
+
+// Fused loss reduction of the row-LSE kernels: every block leaves the sum of its rows' terms in `partials`, the block
+// that finishes last adds them up in index order (deterministic) and resets `counter`.  256 threads, all call.
+__device__ __forceinline__ void fused_loss_tail(float block_sum, float loss_scale, float* __restrict__ loss,
+                                                float* __restrict__ partials, unsigned int* __restrict__ counter) {
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = block_sum;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  __shared__ float red[256];
+  float acc = 0.f;                                     // fixed assignment of partials to threads, fixed tree
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += 256) acc += __ldcg(partials + i);
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    loss[0] = loss_scale * red[0];
+    *counter = 0u;
+  }
 }
 
 // Row log-sum-exp from the slot partials: one WARP per row, lanes stride over the slots (coalesced;
@@ -673,32 +897,115 @@ lse_rows_kernel(const float2* __restrict__ part, int slots, const float2* __rest
   }
   if (loss == nullptr) return;
   __shared__ float warp_term[8];
-  __shared__ bool last;
   if (lane == 0) warp_term[threadIdx.x >> 5] = term;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float sum = 0.f;
+  float sum = 0.f;
+  if (threadIdx.x == 0)
     for (int w = 0; w < 8; ++w) sum += warp_term[w];
-    partials[blockIdx.x] = sum;
-    __threadfence();
-    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  fused_loss_tail(sum, loss_scale, loss, partials, counter);
+}
+
+// The same for the symmetric forward (SymLseEpilogue): plain sums against the common reference M.  A block takes 32
+// consecutive rows (one 256-row tile holds them all): the column sums of the tiles above the rows' own tile are read
+// slot by slot as whole 128-byte lines (lane = row), the rows' own slots row by row; then the queue partials, the LSE
+// and the loss term as above.  Falls back to the (max, sum) partials of the full-matrix launch when that one ran.
+__global__ void __launch_bounds__(256)
+lse_rows_sym_kernel(const float* __restrict__ rowpart, const float* __restrict__ colpart, int col_pitch, int row_slots,
+                    const unsigned int* __restrict__ ctl, float scale_log2, const float2* __restrict__ part, int slots,
+                    const float2* __restrict__ part_q, int slots_q, int rows_q, const float* __restrict__ pos, int rows,
+                    float* __restrict__ lse, float* __restrict__ lse2, float loss_scale, float* __restrict__ loss,
+                    float* __restrict__ partials, unsigned int* __restrict__ counter) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * 32;
+  const unsigned int bits = __ldg(ctl + kCtlBoundBits);
+  const float mref = bounded_reference(scale_log2, bits);
+  const bool sym = 2.f * mref <= kBoundedSpan;
+  __shared__ float colsum[8][33];
+  __shared__ float warp_term[8];
+  const int tile = row0 >> 8;
+  float own[4] = {0.f, 0.f, 0.f, 0.f};   // this lane's share of the four rows' own slots
+  if (sym) {
+    // Every load of a thread is issued before the first one is used (one L2 round trip instead of one per slot: the
+    // kernel is a latency chain, not a bandwidth problem -- 10 MB of partials); the sums run in a fixed order.
+    const float* cp = colpart + row0 + lane;
+    float x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int s = warp + 8 * i;
+      x[i] = s < 8 * tile ? __ldg(cp + static_cast<size_t>(s) * col_pitch) : 0.f;
+    }
+    float y[4][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float* rp = rowpart + static_cast<size_t>(row0 + warp * 4 + r) * row_slots;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int t = 2 * tile + lane + 32 * i;
+        y[r][i] = t < row_slots ? rp[t] : 0.f;
+      }
+    }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) { a0 += x[i]; a1 += x[i + 1]; a2 += x[i + 2]; a3 += x[i + 3]; }
+    colsum[warp][lane] = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      own[r] = y[r][0] + y[r][1];
+      for (int t = 2 * tile + lane + 64; t < row_slots; t += 32)   // (more than 64 slots: 2N > 8192)
+        own[r] += rowpart[static_cast<size_t>(row0 + warp * 4 + r) * row_slots + t];
+    }
   }
   __syncthreads();
-  if (!last) return;
-  __threadfence();
-  __shared__ float red[256];
-  float acc = 0.f;                                     // fixed assignment of partials to threads, fixed tree
-  for (unsigned int i = threadIdx.x; i < gridDim.x; i += 256) acc += __ldcg(partials + i);
-  red[threadIdx.x] = acc;
+  float term = 0.f;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int ro = warp * 4 + r, row = row0 + ro;
+    float m = -INFINITY, l = 0.f, total = 0.f;
+    if (sym) {
+      float sum = own[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += colsum[w][ro];   // (broadcast reads: every lane ends up with the row's total)
+      total = sum;
+      if (lane == 0 && sum > 0.f) { m = mref; l = sum; }
+    } else {
+      for (int s = lane; s < slots; s += 32) {
+        const float2 p = part[static_cast<size_t>(row) * slots + s];
+        lse_combine(m, l, p.x, p.y);
+      }
+    }
+    float v;
+    if (sym && part_q == nullptr) {
+      v = mref + log2f(total);   // no queue: nothing to combine with
+    } else {
+      if (part_q != nullptr) {
+        const int rq = row % rows_q;
+        for (int s = lane; s < slots_q; s += 32) {
+          const float2 p = part_q[static_cast<size_t>(rq) * slots_q + s];
+          lse_combine(m, l, p.x, p.y);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+        const float l2 = __shfl_xor_sync(0xffffffffu, l, o);
+        lse_combine(m, l, m2, l2);
+      }
+      v = m + log2f(l);
+    }
+    if (lane == 0) {
+      lse2[row] = v;
+      lse[row] = v * kLn2;
+    }
+    term += v * kLn2 - pos[row];
+  }
+  if (lane == 0) warp_term[warp] = term;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    loss[0] = loss_scale * red[0];
-    *counter = 0u;
-  }
+  float sum = 0.f;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < 8; ++w) sum += warp_term[w];
+  fused_loss_tail(sum, loss_scale, loss, partials, counter);
 }
 
 // loss = scale * sum_i (lse_i - pos_i)   (contrastive_loss.py:92 sum/2; :24,:42 mean).  One block, fixed
