@@ -312,10 +312,16 @@ def bench_infonce(torch, drs_b200, dev, peaks, n=4096, dim=768, temperature=0.05
         graph_ms = None
     # algorithmic flops: S = F F^T forward (2 (2N)^2 D), backward recompute + dF = H F (2 x 2 (2N)^2 D)
     flops = 3 * 2.0 * (2 * n) ** 2 * dim
+    tiles = 2 * n // 256
+    tri = tiles * (tiles + 1) // 2 / float(tiles * tiles) if (2 * n) % 256 == 0 else 1.0
     return {"workload": f"NCELoss fwd+bwd, batch {n} x {dim} (2N = {2 * n} rows), T = {temperature}, bf16 MMA / fp32 softmax",
             "ms_per_step": ms, "cuda_graph_replay_ms_per_step": graph_ms, "steps_per_s": 1e3 / ms,
             "tflops": flops / (ms * 1e-3) / 1e12,
             "mma_frac": flops / (ms * 1e-3) / 1e12 / peaks["tflops"],
+            "executed_mma_flops": flops * (2 * tri + 1) / 3,
+            "flops_note": "tflops / mma_frac count the ALGORITHMIC flops of the three full-matrix products; S = F F^T and H are "
+                          "symmetric, so the forward and the gradient-of-logits GEMM run only the 256 x 256 tiles on and above "
+                          f"the diagonal ({tri:.3f} of them) and the step executes executed_mma_flops",
             "forward_logit_bytes_not_materialised": 4 * (2 * n) ** 2,
             "backward_grad_logit_bytes_written": ((2 * n // 256) * (2 * n // 256 + 1) // 2) * 256 * 256 * 2,
             "backward_grad_logit_note": "H = dL/dlogits is symmetric: only its 256 x 256 tiles on and above the diagonal are computed and "

@@ -63,7 +63,7 @@ struct Options {
   int round_barrier = 1;
   int seed_thresholds = 1;
   int symmetric_grad = 2;   // InfoNCE backward: 0 full H, 1 upper tiles computed + mirrored stores, 2 upper tiles only (dF reads transposed)
-  int symmetric_lse = 1;    // InfoNCE forward: only the tiles of S = F F^T on and above the diagonal (whole 256-row tiles, bounded logits)
+  int symmetric_lse = 1;    // InfoNCE forward: only the tiles of S = F F^T on and above the diagonal (whole 256-row tiles, bounded logits): 0 off, 1 when it pays, 2 always
   int tma_store = 1;       // InfoNCE backward: the gradient-of-logits tiles leave through TMA stores
   int fp32_tile = 128;     // B-tile width of the fp32 tensor-core scan: 128 (two accumulator stages: 0.66 ms on config 0) or 256 (one: 0.73 ms)
   int m_block = 0;         // search: A tiles per super-block of the unit order: 0 auto (= clusters), -1 off

@@ -270,6 +270,36 @@ def test_shared_exponential_form_and_its_fallback(temp, spread, klen):
         _assert_rows_close(dk.numpy(), rdk.numpy(), "bf16")
 
 
+@pytest.mark.parametrize("n,dim,klen,temp", [(128, 128, 512, 0.05), (512, 64, 0, 0.05), (1024, 128, 256, 0.07), (2048, 64, 0, 0.05),
+                                             (512, 128, 0, 0.01)])
+def test_symmetric_forward_matches_the_full_matrix_forward(n, dim, klen, temp):
+    """Forward over the tiles of F F^T on and above the diagonal only (SymLseEpilogue: row sums and, through a
+    transposing warp butterfly, column sums against one bounded reference) against the full-matrix forward with
+    running maxima: same loss to fp32 summation order, same gradients (they depend on the LSEs), both equal to the
+    oracle.  Forced on (tune.symmetric_lse = 2) because by default it is used only from 2N = 4096 up.  T = 0.01 makes the
+    logits' span exceed the bound: the symmetric launch then walks the full matrix itself."""
+    g = torch.Generator().manual_seed(31)
+    q = torch.nn.functional.normalize(torch.randn(n, dim, generator=g), dim=1)
+    k = torch.nn.functional.normalize(torch.randn(n, dim, generator=g) * 0.5 + q, dim=1)
+    queue = torch.nn.functional.normalize(torch.randn(dim, klen, generator=g), dim=0) if klen else None
+    res = {}
+    try:
+        for mode in (2, 0):
+            drs_b200.set_option("tune.symmetric_lse", mode)
+            res[mode] = _run(q, k, queue, temp, "bf16")
+    finally:
+        drs_b200.set_option("tune.symmetric_lse", 1)
+    (loss_s, dq_s, dk_s), (loss_f, dq_f, dk_f) = res[2], res[0]
+    assert abs(loss_s.item() - loss_f.item()) <= 2e-6 * abs(loss_f.item())
+    scale = max(dq_f.abs().max().item(), dk_f.abs().max().item())
+    assert (dq_s - dq_f).abs().max().item() <= 2e-3 * scale and (dk_s - dk_f).abs().max().item() <= 2e-3 * scale
+    qb, kb = q.bfloat16().float(), k.bfloat16().float()
+    rl, rdq, rdk = infonce.nce_info_loss(qb, kb, queue.bfloat16().float() if klen else None, temp, dtype=torch.float64)
+    assert abs(loss_s.item() - rl.item()) <= 1e-4 * abs(rl.item())
+    _assert_rows_close(dq_s.numpy(), rdq.numpy(), "bf16")
+    _assert_rows_close(dk_s.numpy(), rdk.numpy(), "bf16")
+
+
 def test_loss_step_is_cuda_graph_capturable():
     """Forward + backward of NCELoss captured once in a CUDA graph and replayed on new embeddings: same loss and
     gradients as the eager call (a trainer can take the ~20 small launches off the host)."""
