@@ -41,7 +41,13 @@ const char* drs_last_error(void);
  * stream at a time.
  * "tune.k_split" (default 0 = auto; 1 = off; n > 1 = n slices): the loss gradients wrt q through a long K
  * (dq = Hq x queue, dq = W x prototypes: one or two output tiles, K = queue length) are computed as K slices on
- * many clusters and summed in slice order (deterministic).  Set it BEFORE the *_workspace_bytes query of the call. */
+ * many clusters and summed in slice order (deterministic).  Set it BEFORE the *_workspace_bytes query of the call.
+ * "tune.symmetric_lse" (default 1 = when it shortens the makespan, from 2N = 4096 rows; 0 = never; 2 = always): the bf16
+ * InfoNCE forward computes only the tiles of F F^T on and above the diagonal (whole 256-row tiles) against one bounded
+ * reference; logits whose span exceeds the bound (checked on the device) take the full-matrix schedule inside the same
+ * launch.  Changes the workspace size: set it BEFORE drs_infonce_workspace_bytes.  "tune.symmetric_grad" (default 2): the
+ * same for the gradient-of-logits matrix of the backward (0 = full matrix).  "tune.triangle_order": 0 contiguous pieces
+ * of the tile triangle per cluster (default), 1 round-robin. */
 int drs_set_option(const char* name, int value);
 /* Debug: {flag, tag, block, thread, parity, extra} of the last pipeline wait that timed out (a
  * kernel whose mbarrier wait exceeds a few seconds records this in mapped host memory and traps,

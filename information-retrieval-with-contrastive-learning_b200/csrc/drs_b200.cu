@@ -64,6 +64,7 @@ struct Options {
   int seed_thresholds = 1;
   int symmetric_grad = 2;   // InfoNCE backward: 0 full H, 1 upper tiles computed + mirrored stores, 2 upper tiles only (dF reads transposed)
   int symmetric_lse = 1;    // InfoNCE forward: only the tiles of S = F F^T on and above the diagonal (whole 256-row tiles, bounded logits): 0 off, 1 when it pays, 2 always
+  int triangle_order = 0;   // symmetric InfoNCE GEMMs: 0 contiguous pieces of the tile triangle per cluster, 1 round-robin (TriangleWalk)
   int tma_store = 1;       // InfoNCE backward: the gradient-of-logits tiles leave through TMA stores
   int fp32_tile = 128;     // B-tile width of the fp32 tensor-core scan: 128 (two accumulator stages: 0.66 ms on config 0) or 256 (one: 0.73 ms)
   int m_block = 0;         // search: A tiles per super-block of the unit order: 0 auto (= clusters), -1 off
@@ -229,6 +230,7 @@ drs::GemmShape plan_shape(int64_t rows_a, int64_t rows_b, int dim_k_blocks, int 
   s.epi_tma_store = 0;
   s.a_sym = 0;
   s.skip_below_diagonal = 0;
+  s.tri_order = g_opt.triangle_order;
   s.k_splits = 1;
   s.kb_per_split = dim_k_blocks;
   return s;
@@ -621,6 +623,7 @@ int drs_set_option(const char* name, int value) {
   else if (!strcmp(name, "tune.seed_thresholds")) g_opt.seed_thresholds = value;
   else if (!strcmp(name, "tune.symmetric_grad")) g_opt.symmetric_grad = value;
   else if (!strcmp(name, "tune.symmetric_lse")) g_opt.symmetric_lse = value;
+  else if (!strcmp(name, "tune.triangle_order")) g_opt.triangle_order = value;
   else if (!strcmp(name, "tune.k_split")) g_opt.k_split = value;
   else if (!strcmp(name, "tune.cooperative")) g_opt.cooperative = value;
   else if (!strcmp(name, "search.fp32_mode")) g_opt.fp32_mode = value;
@@ -645,6 +648,7 @@ int drs_get_option(const char* name, int* value) {
   else if (!strcmp(name, "tune.seed_thresholds")) *value = g_opt.seed_thresholds;
   else if (!strcmp(name, "tune.symmetric_grad")) *value = g_opt.symmetric_grad;
   else if (!strcmp(name, "tune.symmetric_lse")) *value = g_opt.symmetric_lse;
+  else if (!strcmp(name, "tune.triangle_order")) *value = g_opt.triangle_order;
   else if (!strcmp(name, "tune.k_split")) *value = g_opt.k_split;
   else if (!strcmp(name, "tune.cooperative")) *value = g_opt.cooperative;
   else if (!strcmp(name, "search.fp32_mode")) *value = g_opt.fp32_mode;

@@ -54,6 +54,7 @@ struct GemmShape {
   int skip_below_diagonal;      // A == B, square (A tile rows == B tile rows), symmetric output: only the tiles on and
                                 // above the diagonal are computed, dealt to the clusters as contiguous pieces of the
                                 // row-major triangle (TriangleWalk); the epilogue writes both halves
+  int tri_order;                // skip_below_diagonal: how the triangle's tiles are dealt to the clusters (TriangleWalk)
   int k_splits;                 // > 1: split-K -- unit u covers K blocks [ks * kb_per_split, ...) of tile (u % base units) with
   int kb_per_split;             // ks = u / base units, and the epilogue functor is handed split + num_splits * ks (a long-K
                                 // GEMM with one or two output tiles, e.g. dq = Hq x queue at N = 128, K = 12 544, would
@@ -111,23 +112,34 @@ __device__ __forceinline__ void unit_to_tile(const GemmShape& shp, int u, int& m
   m = m0 + r - s * mb;
 }
 
-// The tiles on and above the diagonal of a square tile grid (t >= m), row-major, cut into `parts` contiguous,
-// equally long pieces: piece `part` walks its share.  Consecutive tiles mostly share the A tile (m).
+// The tiles on and above the diagonal of a square tile grid (t >= m) in row-major order, dealt to `parts` clusters:
+//   order 0: contiguous, equally long pieces -- consecutive tiles of a cluster mostly share the A tile (m);
+//   order 1: round-robin (tile i goes to cluster i mod parts) -- the clusters that run at the same time work on ~2.3
+//            neighbouring rows of the triangle: they share two or three A tiles and overlapping B tiles.
 struct TriangleWalk {
-  int m, t, left, tiles_m;
-  __device__ TriangleWalk(int num_m_tiles, unsigned part, unsigned parts) : tiles_m(num_m_tiles) {
+  int m, t, left, tiles_m, step;
+  __device__ TriangleWalk(int num_m_tiles, unsigned part, unsigned parts, int order = 0) : tiles_m(num_m_tiles) {
     const long long live = static_cast<long long>(num_m_tiles) * (num_m_tiles + 1) / 2;
-    long long lo = live * part / parts;
-    const long long hi = live * (part + 1) / parts;
-    left = static_cast<int>(hi - lo);
+    long long lo;
+    if (order == 1) {
+      lo = part;
+      step = static_cast<int>(parts);
+      left = lo < live ? static_cast<int>((live - lo + parts - 1) / parts) : 0;
+    } else {
+      lo = live * part / parts;
+      step = 1;
+      left = static_cast<int>(live * (part + 1) / parts - lo);
+    }
     m = 0;
     while (m < num_m_tiles && lo >= num_m_tiles - m) { lo -= num_m_tiles - m; ++m; }
     t = m + static_cast<int>(lo);
   }
   __device__ bool valid() const { return left > 0; }
   __device__ void next() {
-    --left;
-    if (++t == tiles_m) { ++m; t = m; }
+    if (--left <= 0) return;
+    int pos = t - m + step;
+    while (pos >= tiles_m - m) { pos -= tiles_m - m; ++m; }
+    t = m + pos;
   }
 };
 
@@ -306,7 +318,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       // it the groups drift apart by more than the L2 can hold and the corpus is re-read ~18x).
       // Every CTA of the grid is resident (checked and enforced by the launcher), so the spin cannot deadlock.
       if (triangle) {
-        for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters); w.valid(); w.next()) load_tile(w.m, w.t, 0, shp.num_k_blocks);
+        for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters, shp.tri_order); w.valid(); w.next()) load_tile(w.m, w.t, 0, shp.num_k_blocks);
       } else {
         const int num_rounds = (num_units + static_cast<int>(nclusters) - 1) / static_cast<int>(nclusters);
         for (int round = 0; round < num_rounds; ++round) {
@@ -390,7 +402,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
       };
       if (triangle) {
-        for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters); w.valid(); w.next()) mma_tile(0, 0, shp.num_k_blocks);
+        for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters, shp.tri_order); w.valid(); w.next()) mma_tile(0, 0, shp.num_k_blocks);
       } else {
         for (int u = cluster; u < num_units; u += nclusters) {
           int m, s, kb0, kb1;
@@ -462,7 +474,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     };
     if (triangle) {
       // every tile is its own unit (the functors used with this schedule keep no state across tiles)
-      for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters); w.valid(); w.next()) {
+      for (TriangleWalk w(shp.num_m_tiles, cluster, nclusters, shp.tri_order); w.valid(); w.next()) {
         const int row = (w.m * CG + static_cast<int>(cta_rank)) * Cfg::BM + row_in_tile;
         epi.begin_unit(ep, row, w.m, w.t);
         epi_tile(row, w.t);
