@@ -169,7 +169,7 @@ struct SymLseEpilogue {
   struct Params {
     float* rowpart;            // [rows][row_slots]  sum_j 2^(y_ij - M) over the columns of slot (tile t, column group)
     float* colpart;            // [tiles * 8][col_pitch]  entry (m * 8 + w, j): sum_i 2^(y_ij - M) over the 32 rows of warp w of A tile m
-    int col_pitch;             // rows + 32: consecutive slots of a column are NOT a power of two apart (L2 slice camping)
+    int col_pitch;             // rows + 32 (slots of a column not a power of two apart; measured: no different from a pitch of `rows`)
     float* pos;                // [rows] positive logit in natural units
     const unsigned int* ctl;   // control words (M)
     int rows;                  // 2N, a multiple of the 256-row tile
