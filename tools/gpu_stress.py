@@ -2,7 +2,8 @@
 """Randomised stress (test tooling): many search shapes where claims' units run over several rounds (threshold seeds,
 round barrier, A super-blocks, adaptive passes) and many InfoNCE shapes (symmetric H, transposed reads), each compared
 with an exact reference computed on the GPU in fp32 / fp64.  Prints one line per failure and a summary.
-    python tools/gpu_stress.py [search cases=120] [loss cases=40] [seed=0]"""
+    python tools/gpu_stress.py [search cases=120] [loss cases=40] [seed=0]      (DRS_OPTIONS=name=value,... sets engine
+options, e.g. tune.symmetric_lse=2 puts every whole-tile batch on the symmetric forward)"""
 import os
 import sys
 
@@ -17,6 +18,9 @@ n_search = int(sys.argv[1]) if len(sys.argv) > 1 else 120
 n_loss = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 rng = np.random.RandomState(int(sys.argv[3]) if len(sys.argv) > 3 else 0)
 unit = lambda x: torch.nn.functional.normalize(x, dim=1)
+for opt in os.environ.get("DRS_OPTIONS", "").split(","):
+    if "=" in opt:
+        drs.set_option(opt.split("=")[0], int(opt.split("=")[1]))
 
 
 def exact_topk(q, c, k):
@@ -72,10 +76,10 @@ print(f"search: {n_search - fails} / {n_search} ok", flush=True)
 
 lfails = 0
 for case in range(n_loss):
-    n = int(rng.choice([4, 64, 128, 256, 384, 512, 1024, 1536, 2048]))
+    n = int(rng.choice([4, 64, 128, 256, 384, 512, 1024, 1536, 2048, 4096]))   # (4096: the symmetric forward by default)
     dim = int(rng.choice([64, 128, 256, 768]))      # (narrower rows: bf16 rounding alone moves gradient rows by ~3 %, 'auto' takes fp32)
     klen = int(rng.choice([0, 0, 64, 512, 2048, 4104, 12544]))     # long queues: dq = Hq x queue runs split-K
-    temp = float(rng.choice([0.05, 0.07, 0.2]))
+    temp = float(rng.choice([0.05, 0.07, 0.2, 0.02]))   # (0.02: logits beyond the bound of the symmetric forward)
     g = torch.Generator(device=dev).manual_seed(5000 + case)
     q = unit(torch.randn(n, dim, generator=g, device=dev)).requires_grad_(True)
     kk = unit(torch.randn(n, dim, generator=g, device=dev) * 0.5 + q.detach()).requires_grad_(True)
