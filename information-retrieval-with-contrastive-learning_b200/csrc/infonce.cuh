@@ -934,6 +934,8 @@ lse_rows_sym_kernel(const float* __restrict__ rowpart, const float* __restrict__
       const int s = warp + 8 * i;
       x[i] = s < 8 * tile ? __ldg(cp + static_cast<size_t>(s) * col_pitch) : 0.f;
     }
+    float beyond = 0.f;   // (more than 256 column slots: 2N > 8192)
+    for (int s = 256 + warp; s < 8 * tile; s += 8) beyond += __ldg(cp + static_cast<size_t>(s) * col_pitch);
     float y[4][2];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -947,7 +949,7 @@ lse_rows_sym_kernel(const float* __restrict__ rowpart, const float* __restrict__
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) { a0 += x[i]; a1 += x[i + 1]; a2 += x[i + 2]; a3 += x[i + 3]; }
-    colsum[warp][lane] = (a0 + a1) + (a2 + a3);
+    colsum[warp][lane] = ((a0 + a1) + (a2 + a3)) + beyond;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       own[r] = y[r][0] + y[r][1];

@@ -111,6 +111,37 @@ def test_config4_full_size_forward_backward():
     _assert_rows_close(dk.numpy(), rdk.numpy(), "bf16")
 
 
+def test_batch_8192_beyond_one_pass_of_partials():
+    """2N = 16 384 rows: 64 tile rows -- more row slots (128) and column slots (up to 504) than one batch of loads of
+    the symmetric forward's row kernel covers.  Loss and a sample of gradient rows against the closed form in float64
+    on the GPU, fed the same bf16-rounded embeddings."""
+    n, dim, temp = 8192, 128, 0.05
+    g = torch.Generator(device=DEV).manual_seed(77)
+    q = torch.nn.functional.normalize(torch.randn(n, dim, generator=g, device=DEV), dim=1).bfloat16().float().requires_grad_(True)
+    k = torch.nn.functional.normalize(torch.randn(n, dim, generator=g, device=DEV) * 0.5 + q.detach(), dim=1).bfloat16().float().requires_grad_(True)
+    loss = drs_b200.NCELoss({"temperature": temp, "precision": "bf16"})(q, k, None)
+    loss.backward()
+    f = torch.cat([q.detach(), k.detach()]).double()
+    lse = torch.empty(2 * n, dtype=torch.float64, device=DEV)
+    for r0 in range(0, 2 * n, 2048):                      # row blocks: the 16 384^2 float64 matrix never exists
+        sm = (f[r0:r0 + 2048] @ f.T) / temp
+        sm[torch.arange(2048, device=DEV), torch.arange(r0, r0 + 2048, device=DEV)] = float("-inf")
+        lse[r0:r0 + 2048] = torch.logsumexp(sm, 1)
+    pos = (f[:n] * f[n:]).sum(1) / temp
+    ref = (lse.sum() - 2 * pos.sum()) / 2
+    assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())
+    rows = torch.tensor([0, 1, 255, 256, 4095, 4096, 8191], device=DEV)      # dq rows: d/dq_i = sum_j H_ij f_j over both halves
+    p_rows = torch.exp((f[rows] @ f.T) / temp - lse[rows, None])             # P[i, :]
+    p_cols = torch.exp((f[rows] @ f.T) / temp - lse[None, :])                # P[:, i] (S symmetric)
+    h = p_rows + p_cols
+    h[torch.arange(len(rows), device=DEV), rows] = 0.0
+    h[torch.arange(len(rows), device=DEV), rows + n] -= 2.0
+    ref_dq = (h @ f) / (2 * temp)
+    got = q.grad[rows].double()
+    rel = (got - ref_dq).norm(dim=1) / ref_dq.norm(dim=1)
+    assert rel.max().item() <= 3e-2, rel
+
+
 def test_module_is_stateless_and_k_no_grad_ok():
     crit = drs_b200.NCELoss({"temperature": 0.05})
     assert len(crit.state_dict()) == 0
