@@ -57,6 +57,10 @@ int drs_get_option(const char* name, int* value);
 /* Debug: how many clusters of `cluster_size` CTAs of the scan kernel (one CTA per SM, ~198 KB of shared memory)
  * the current device can hold at once (cudaOccupancyMaxActiveClusters). */
 int drs_debug_max_clusters(int cluster_size, int* out);
+/* Debug (host only, no GPU needed): the tiles (m, t), t >= m, of a `tiles` x `tiles` symmetric tile grid that cluster `part`
+ * of `parts` walks in the symmetric InfoNCE GEMMs (order 0: contiguous pieces, 1: round-robin; "tune.triangle_order").
+ * Writes up to `capacity` (m, t) pairs to out_mt and the true number to *count. */
+int drs_debug_triangle_walk(int tiles, int parts, int part, int order, int* out_mt, int capacity, int* count);
 
 /*
  * Dense claim x corpus scoring with fused top-k select.

@@ -24,6 +24,7 @@ _SIGNATURES = {
     "drs_set_option": (c_int, [ctypes.c_char_p, c_int]),
     "drs_get_option": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int)]),
     "drs_debug_max_clusters": (c_int, [c_int, ctypes.POINTER(c_int)]),
+    "drs_debug_triangle_walk": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_int)]),
     "drs_debug_hang_report": (c_int, [ctypes.POINTER(ctypes.c_uint * 6)]),
     "drs_search_workspace_bytes": (c_int, [c_i64, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_sz)]),
     "drs_search": (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),

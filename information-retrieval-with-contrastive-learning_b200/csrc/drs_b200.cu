@@ -587,6 +587,18 @@ int drs_debug_hang_report(unsigned int out[6]) {
   return DRS_OK;
 }
 
+int drs_debug_triangle_walk(int tiles, int parts, int part, int order, int* out_mt, int capacity, int* count) {
+  if (tiles <= 0 || parts <= 0 || part < 0 || part >= parts || !count || (capacity > 0 && !out_mt))
+    return fail(DRS_ERR_INVALID, "drs_debug_triangle_walk: bad arguments");
+  int n = 0;
+  for (drs::TriangleWalk w(tiles, static_cast<unsigned>(part), static_cast<unsigned>(parts), order); w.valid(); w.next()) {
+    if (n < capacity) { out_mt[2 * n] = w.m; out_mt[2 * n + 1] = w.t; }
+    ++n;
+  }
+  *count = n;
+  return DRS_OK;
+}
+
 int drs_debug_max_clusters(int cluster_size, int* out) {
   if (!out || cluster_size < 1 || cluster_size > 16) return fail(DRS_ERR_INVALID, "bad argument");
   using Cfg = drs::GemmCfg<2>;

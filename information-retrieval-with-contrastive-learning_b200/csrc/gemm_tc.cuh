@@ -118,7 +118,7 @@ __device__ __forceinline__ void unit_to_tile(const GemmShape& shp, int u, int& m
 //            neighbouring rows of the triangle: they share two or three A tiles and overlapping B tiles.
 struct TriangleWalk {
   int m, t, left, tiles_m, step;
-  __device__ TriangleWalk(int num_m_tiles, unsigned part, unsigned parts, int order = 0) : tiles_m(num_m_tiles) {
+  __host__ __device__ TriangleWalk(int num_m_tiles, unsigned part, unsigned parts, int order = 0) : tiles_m(num_m_tiles) {
     const long long live = static_cast<long long>(num_m_tiles) * (num_m_tiles + 1) / 2;
     long long lo;
     if (order == 1) {
@@ -134,8 +134,8 @@ struct TriangleWalk {
     while (m < num_m_tiles && lo >= num_m_tiles - m) { lo -= num_m_tiles - m; ++m; }
     t = m + static_cast<int>(lo);
   }
-  __device__ bool valid() const { return left > 0; }
-  __device__ void next() {
+  __host__ __device__ bool valid() const { return left > 0; }
+  __host__ __device__ void next() {
     if (--left <= 0) return;
     int pos = t - m + step;
     while (pos >= tiles_m - m) { pos -= tiles_m - m; ++m; }

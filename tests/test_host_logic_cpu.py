@@ -178,3 +178,32 @@ def test_clustering_has_no_cpu_path():
 
     with pytest.raises(RuntimeError, match="no CPU path"):
         drs_b200.update_centroids(torch.randn(10, 8), torch.zeros(10, dtype=torch.int64), torch.randn(3, 8))
+
+
+def test_triangle_walk_covers_every_symmetric_tile_once():
+    """The symmetric InfoNCE GEMMs (forward LSE, gradient-of-logits) compute only the tiles (m, t), t >= m, of the
+    square tile grid, dealt to the clusters by TriangleWalk (gemm_tc.cuh) -- run here on the host through
+    drs_debug_triangle_walk: every tile exactly once, for both orders; contiguous pieces differ by at most one tile
+    and stay in row-major order; round-robin hands tile i to cluster i mod parts."""
+    import ctypes
+    from drs_b200 import _lib
+    lib = _lib.load()
+    for tiles in (1, 2, 3, 8, 31, 32, 64):
+        live = tiles * (tiles + 1) // 2
+        order_all = [(m, t) for m in range(tiles) for t in range(m, tiles)]
+        for parts in (1, 7, 74, 600):
+            for order in (0, 1):
+                seen, sizes = [], []
+                for part in range(parts):
+                    buf = (ctypes.c_int * (2 * live))()
+                    cnt = ctypes.c_int(0)
+                    _lib.check(lib.drs_debug_triangle_walk(tiles, parts, part, order, buf, live, ctypes.byref(cnt)))
+                    walk = [(buf[2 * i], buf[2 * i + 1]) for i in range(cnt.value)]
+                    sizes.append(len(walk))
+                    if order == 0:
+                        assert walk == sorted(walk)
+                    else:
+                        assert walk == order_all[part::parts]
+                    seen += walk
+                assert sorted(seen) == order_all, (tiles, parts, order)
+                assert max(sizes) - min(sizes) <= 1
