@@ -331,6 +331,26 @@ def test_symmetric_forward_matches_the_full_matrix_forward(n, dim, klen, temp):
     _assert_rows_close(dk_s.numpy(), rdk.numpy(), "bf16")
 
 
+def test_round_robin_tile_order_gives_the_same_bits():
+    """tune.triangle_order = 1 deals the tiles of the symmetric GEMMs round-robin instead of in contiguous pieces: which
+    cluster computes a tile must not matter (partials are placed by tile coordinates, sums run in a fixed order)."""
+    n, dim = 1024, 128
+    g = torch.Generator().manual_seed(41)
+    q = torch.nn.functional.normalize(torch.randn(n, dim, generator=g), dim=1)
+    k = torch.nn.functional.normalize(torch.randn(n, dim, generator=g) * 0.5 + q, dim=1)
+    res = {}
+    try:
+        drs_b200.set_option("tune.symmetric_lse", 2)
+        for order in (0, 1):
+            drs_b200.set_option("tune.triangle_order", order)
+            res[order] = _run(q, k, None, 0.05, "bf16")
+    finally:
+        drs_b200.set_option("tune.triangle_order", 0)
+        drs_b200.set_option("tune.symmetric_lse", 1)
+    assert res[0][0].item() == res[1][0].item()
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+
+
 def test_loss_step_is_cuda_graph_capturable():
     """Forward + backward of NCELoss captured once in a CUDA graph and replayed on new embeddings: same loss and
     gradients as the eager call (a trainer can take the ~20 small launches off the host)."""
