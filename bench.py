@@ -310,6 +310,33 @@ def bench_infonce(torch, drs_b200, dev, peaks, n=4096, dim=768, temperature=0.05
         graph_ms = e0.elapsed_time(e1) / reps
     except Exception:  # noqa: BLE001  (graph capture is an extra; the eager number stands on its own)
         graph_ms = None
+    # parity of what was just timed, outside the timed region: the closed form of contrastive_loss.py:56-93 with
+    # torch fp32 matmul + logsumexp + autograd on the GPU (not the oracle, not the product)
+    parity = None
+    try:
+        q.grad = None
+        kk.grad = None
+        loss = step()
+        torch.cuda.synchronize()
+        qr, kr = q.detach().clone().requires_grad_(True), kk.detach().clone().requires_grad_(True)
+        f = torch.cat([qr, kr])
+        sm = (f @ f.T) / temperature
+        sm = sm.masked_fill(torch.eye(2 * n, dtype=torch.bool, device=dev), float("-inf"))
+        pos = torch.arange(2 * n, device=dev).roll(n)
+        ref = (torch.logsumexp(sm, 1) - sm[torch.arange(2 * n, device=dev), pos]).sum() / 2
+        ref.backward()
+        del sm, f
+
+        def worst_row(a, b):
+            rn = b.norm(dim=1)
+            return float(((a - b).norm(dim=1) / rn.clamp_min(float(rn.max()) * 1e-6)).max())
+        loss_rel = abs(float(loss) - float(ref)) / abs(float(ref))
+        row_rel = max(worst_row(q.grad, qr.grad), worst_row(kk.grad, kr.grad))
+        parity = {"loss_rel_err": loss_rel, "grad_worst_row_rel_err": row_rel, "ok": bool(loss_rel <= 2e-2 and row_rel <= 3e-2),
+                  "method": "loss and every gradient row of the timed step vs torch fp32 matmul + logsumexp + autograd on the "
+                            "same embeddings (bars: 2e-2 on the loss, 3e-2 relative L2 per gradient row -- the bf16 path)"}
+    except Exception as exc:  # noqa: BLE001
+        parity = {"ok": False, "error": repr(exc)[:200]}
     # algorithmic flops: S = F F^T forward (2 (2N)^2 D), backward recompute + dF = H F (2 x 2 (2N)^2 D)
     flops = 3 * 2.0 * (2 * n) ** 2 * dim
     tiles = 2 * n // 256
@@ -326,7 +353,7 @@ def bench_infonce(torch, drs_b200, dev, peaks, n=4096, dim=768, temperature=0.05
             "backward_grad_logit_bytes_written": ((2 * n // 256) * (2 * n // 256 + 1) // 2) * 256 * 256 * 2,
             "backward_grad_logit_note": "H = dL/dlogits is symmetric: only its 256 x 256 tiles on and above the diagonal are computed and "
                                         "stored (bf16, once); the dF = H F GEMM reads the others transposed (MN-major tcgen05 operand)",
-            "workspace_bytes": _infonce_workspace_bytes(n, dim)}
+            "workspace_bytes": _infonce_workspace_bytes(n, dim), "parity": parity}
 
 
 def _infonce_workspace_bytes(n, dim):
