@@ -103,7 +103,17 @@ def check(rc: int):
         raise RuntimeError(f"drs_b200 error {rc}: {msg}")
 
 
+_options_epoch = 0
+
+
+def options_epoch() -> int:
+    """bumped by every set_option: callers that cache layout answers (workspace sizes) key them on it"""
+    return _options_epoch
+
+
 def set_option(name: str, value: int):
+    global _options_epoch
+    _options_epoch += 1
     check(load().drs_set_option(name.encode(), int(value)))
 
 

@@ -38,6 +38,48 @@ def _workspace(device, nbytes):
     return buf
 
 
+def _as_f32(t):
+    """detach + fp32 + contiguous; a no-op chain for what a trainer passes (fp32, contiguous) -- below ~4096 x 768 the
+    loss step is bound by host time, so the common case avoids dispatcher round trips that change nothing"""
+    t = t.detach()
+    if t.dtype is not torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _device_guard(dev):
+    """torch.cuda.device(dev) only when dev is not already the current device"""
+    return _NO_GUARD if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+
+_need_cache: dict = {}
+
+
+def _workspace_bytes(query, *key):
+    """cached *_workspace_bytes(...) answers; engine options that change a layout (tune.k_split, tune.symmetric_lse) bump
+    _lib.options_epoch, which is part of the key"""
+    k = (query, _lib.options_epoch(), torch.cuda.current_device()) + key
+    need = _need_cache.get(k)
+    if need is None:
+        out = ctypes.c_size_t(0)
+        _lib.check(getattr(_lib.load(), query)(*key, ctypes.byref(out)))
+        if len(_need_cache) > 256:
+            _need_cache.clear()
+        need = _need_cache[k] = out.value
+    return need
+
+
 def _pick_precision(requested, n, dim, klen):
     """In-batch form: the 2N x 2N gradient matrix needs 2N % 8 == 0 and the queue a 16-byte row pitch.  The
     row x column forms (MoCo queue, prototypes) pass n = 4, klen = 0: their column count may be ragged (the
@@ -67,26 +109,25 @@ class _InfoNceFunction(torch.autograd.Function):
             raise RuntimeError("drs_b200 NCELoss needs CUDA tensors: there is no CPU path")
         if q.shape != k.shape or q.dim() != 2:
             raise ValueError(f"q and k must both be [N, D], got {tuple(q.shape)} and {tuple(k.shape)}")
-        qf = q.detach().contiguous().float()
-        kf = k.detach().contiguous().float()
+        qf = _as_f32(q)
+        kf = _as_f32(k)
         n, dim = qf.shape
         qu = None
         klen = 0
         if queue is not None:
             if queue.dim() != 2 or queue.shape[0] != dim:
                 raise ValueError(f"queue must be [D, K] with D={dim}, got {tuple(queue.shape)}")
-            qu = queue.detach().to(device=q.device).contiguous().float()   # :80 queue.clone().detach()
+            qu = _as_f32(queue if queue.device == q.device else queue.to(device=q.device))   # :80 queue.clone().detach()
             klen = qu.shape[1]
         prec = _pick_precision(precision, n, dim, klen)
         lib = _lib.load()
         dev = q.device
-        with torch.cuda.device(dev):
-            need = ctypes.c_size_t(0)
-            _lib.check(lib.drs_infonce_workspace_bytes(n, dim, klen, prec, ctypes.byref(need)))
+        with _device_guard(dev):
+            need = _workspace_bytes("drs_infonce_workspace_bytes", n, dim, klen, prec)
             # when a backward will follow, the step owns its workspace: the packed operands and row LSEs the
             # forward leaves there are reused by the backward instead of being staged a second time
             keep = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
-            ws = torch.empty(need.value, dtype=torch.uint8, device=dev) if keep else _workspace(dev, need.value)
+            ws = torch.empty(need, dtype=torch.uint8, device=dev) if keep else _workspace(dev, need)
             loss = torch.empty(1, dtype=torch.float32, device=dev)
             lse = torch.empty(2 * n, dtype=torch.float32, device=dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -108,13 +149,12 @@ class _InfoNceFunction(torch.autograd.Function):
         klen = qu.shape[1] if ctx.has_queue else 0
         lib = _lib.load()
         dev = qf.device
-        with torch.cuda.device(dev):
-            need = ctypes.c_size_t(0)
-            _lib.check(lib.drs_infonce_workspace_bytes(n, dim, klen, ctx.prec, ctypes.byref(need)))
-            staged = ctx.staged_ws is not None and ctx.staged_ws.numel() >= need.value
-            ws = ctx.staged_ws if staged else _workspace(dev, need.value)
+        with _device_guard(dev):
+            need = _workspace_bytes("drs_infonce_workspace_bytes", n, dim, klen, ctx.prec)
+            staged = ctx.staged_ws is not None and ctx.staged_ws.numel() >= need
+            ws = ctx.staged_ws if staged else _workspace(dev, need)
             ctx.staged_ws = None            # a second backward through the same graph stages again (H overwrote nothing it needs, but keep it simple)
-            g = grad_out.detach().reshape(1).to(device=dev, dtype=torch.float32).contiguous()
+            g = _as_f32(grad_out if grad_out.device == dev else grad_out.to(device=dev)).reshape(1)
             dq = torch.empty_like(qf)
             dk = torch.empty_like(kf)
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -122,7 +162,9 @@ class _InfoNceFunction(torch.autograd.Function):
             _lib.check(backward(qf.data_ptr(), kf.data_ptr(), qu.data_ptr() if ctx.has_queue else None,
                                                 n, dim, klen, ctx.inv_t, ctx.prec, lse.data_ptr(), g.data_ptr(),
                                                 dq.data_ptr(), dk.data_ptr(), ws.data_ptr(), ws.numel(), stream))
-        return dq.to(ctx.in_dtypes[0]), dk.to(ctx.in_dtypes[1]), None, None, None
+        f32 = torch.float32
+        return (dq if ctx.in_dtypes[0] is f32 else dq.to(ctx.in_dtypes[0]),
+                dk if ctx.in_dtypes[1] is f32 else dk.to(ctx.in_dtypes[1]), None, None, None)
 
 
 def info_nce_loss(q, k, queue=None, temperature=0.05, precision="auto"):

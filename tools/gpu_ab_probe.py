@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Perf probe (test tooling): NCELoss fwd+bwd at 4096 x 768 with an engine option toggled back and forth in ONE process
 (the boxes differ by several per cent, so A/B across runs says little).
-    python tools/gpu_ab_probe.py <option> <value A> <value B> [rounds]"""
+    python tools/gpu_ab_probe.py <option> <value A> <value B> [rounds] [n] [dim]"""
 import os
 import sys
 
@@ -14,7 +14,8 @@ opt, va, vb = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 rounds = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(1337)
-n, dim = 4096, 768
+n = int(sys.argv[5]) if len(sys.argv) > 5 else 4096
+dim = int(sys.argv[6]) if len(sys.argv) > 6 else 768
 unit = lambda x: torch.nn.functional.normalize(x, dim=1)
 q = unit(torch.randn(n, dim, generator=g, device=dev)).requires_grad_(True)
 k = unit(torch.randn(n, dim, generator=g, device=dev) * 0.5 + q.detach()).requires_grad_(True)
@@ -46,4 +47,4 @@ for _ in range(rounds):
         drs.set_option(opt, v)
         res[v].append(timed())
 for v in (va, vb):
-    print(f"{opt}={v}: " + " ".join(f"{t * 1e3:.1f}" for t in res[v]) + f" us/step (min {min(res[v]) * 1e3:.1f})")
+    print(f"n={n} dim={dim} {opt}={v}: " + " ".join(f"{t * 1e3:.1f}" for t in res[v]) + f" us/step (min {min(res[v]) * 1e3:.1f})")
