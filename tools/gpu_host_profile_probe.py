@@ -1,7 +1,17 @@
-import cProfile, pstats, sys, os, io, time
-sys.path.insert(0, "/root/repo")
-import torch
-import drs_b200 as drs
+#!/usr/bin/env python
+"""Perf probe (test tooling): host time of the NCELoss module at the reference's shapes (N = 128, D = 128, queue 12 544) --
+forward and backward separately, then a cProfile of 300 forward + backward steps."""
+import cProfile
+import io
+import os
+import pstats
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import drs_b200 as drs  # noqa: E402
 n, dim, klen = 128, 128, 12544
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(1)
