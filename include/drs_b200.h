@@ -42,7 +42,7 @@ const char* drs_last_error(void);
  * "tune.k_split" (default 0 = auto; 1 = off; n > 1 = n slices): the loss gradients wrt q through a long K
  * (dq = Hq x queue, dq = W x prototypes: one or two output tiles, K = queue length) are computed as K slices on
  * many clusters and summed in slice order (deterministic).  Set it BEFORE the *_workspace_bytes query of the call.
- * "tune.symmetric_lse" (default 1 = when it shortens the makespan, from 2N = 4096 rows; 0 = never; 2 = always): the bf16
+ * "tune.symmetric_lse" (default 1 = when it pays, from 2N = 6144 rows at dim = 768; 0 = never; 2 = always): the bf16
  * InfoNCE forward computes only the tiles of F F^T on and above the diagonal (whole 256-row tiles) against one bounded
  * reference; logits whose span exceeds the bound (checked on the device) take the full-matrix schedule inside the same
  * launch.  Changes the workspace size: set it BEFORE drs_infonce_workspace_bytes.  "tune.symmetric_grad" (default 2): the

@@ -307,7 +307,7 @@ def test_symmetric_forward_matches_the_full_matrix_forward(n, dim, klen, temp):
     """Forward over the tiles of F F^T on and above the diagonal only (SymLseEpilogue: row sums and, through a
     transposing warp butterfly, column sums against one bounded reference) against the full-matrix forward with
     running maxima: same loss to fp32 summation order, same gradients (they depend on the LSEs), both equal to the
-    oracle.  Forced on (tune.symmetric_lse = 2) because by default it is used only from 2N = 4096 up.  T = 0.01 makes the
+    oracle.  Forced on (tune.symmetric_lse = 2) because by default it is used only where it pays (2N >= 6144 at dim = 768).  T = 0.01 makes the
     logits' span exceed the bound: the symmetric launch then walks the full matrix itself."""
     g = torch.Generator().manual_seed(31)
     q = torch.nn.functional.normalize(torch.randn(n, dim, generator=g), dim=1)

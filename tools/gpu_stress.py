@@ -76,7 +76,7 @@ print(f"search: {n_search - fails} / {n_search} ok", flush=True)
 
 lfails = 0
 for case in range(n_loss):
-    n = int(rng.choice([4, 64, 128, 256, 384, 512, 1024, 1536, 2048, 4096]))   # (4096: the symmetric forward by default)
+    n = int(rng.choice([4, 64, 128, 256, 384, 512, 1024, 1536, 2048, 4096]))   # (4096 x 768: the symmetric forward by default)
     dim = int(rng.choice([64, 128, 256, 768]))      # (narrower rows: bf16 rounding alone moves gradient rows by ~3 %, 'auto' takes fp32)
     klen = int(rng.choice([0, 0, 64, 512, 2048, 4104, 12544]))     # long queues: dq = Hq x queue runs split-K
     temp = float(rng.choice([0.05, 0.07, 0.2, 0.02]))   # (0.02: logits beyond the bound of the symmetric forward)
